@@ -1,0 +1,625 @@
+// pvt_api.cu -- the C ABI of include/pvtrace_b200.h on top of the kernels in pvt_kernels.cuh.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC  (csrc/build.py)
+// There is no CPU path in this library: every compute entry fails with an error string if CUDA cannot run it.
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/pvtrace_b200.h"
+#include "pvt_common.cuh"
+#include "pvt_kernels.cuh"
+
+namespace pvt {
+
+static thread_local char g_error[1024] = "";
+char* error_buffer() { return g_error; }
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+}  // namespace pvt
+
+using namespace pvt;
+
+// ---------------------------------------------------------------------------------------------------------
+// Context: the device-resident scene + tally accumulators + event-log buffers of ONE device.
+
+struct pvt_context {
+  int device = 0;
+  int sm_count = 0;
+  Header hdr;
+  int blob_words = 0;
+  int scene_in_smem = 1;
+  size_t smem_bytes = 0;
+  int has_emitter = 0;
+  std::vector<double> host_blob;
+  DeviceBuffer<double> blob;
+  // one allocation of 8-byte words: [distinct R | cross R | sums 8R | bins B | stats NSTATS | work counter 1]
+  DeviceBuffer<u64> tallies;
+  size_t tally_words = 0;
+  DeviceBuffer<double> packed;
+  // event log of the last trace
+  long long log_rows = 0, log_rays = 0;
+  DeviceBuffer<int32_t> counts, hit, container, adjacent, component, source;
+  DeviceBuffer<uint8_t> kind;
+  DeviceBuffer<double> position, direction, normal, wavelength, travelled, duration;
+  int blocks_per_sm[4] = {0, 0, 0, 0};  // per kernel instantiation
+  long long launches = 0;
+
+  int R() const { return hdr.n_recorders; }
+  int B() const { return hdr.total_bins; }
+  u64* d_distinct() { return tallies.ptr; }
+  u64* d_cross() { return tallies.ptr + R(); }
+  double* d_sums() { return reinterpret_cast<double*>(tallies.ptr + 2 * R()); }
+  u64* d_bins() { return tallies.ptr + 10 * R(); }
+  u64* d_stats() { return tallies.ptr + 10 * R() + B(); }
+  u64* d_work() { return tallies.ptr + 10 * R() + B() + PVT_NSTATS; }
+};
+
+static int validate_scene(const pvt_scene_t* S) {
+  if (!S) return fail("scene is NULL");
+  if (S->n_nodes <= 0) return fail("scene has no geometry nodes");
+  if (S->n_nodes > PVT_MAX_NODES) return fail("Engine supports at most %d geometry nodes.", PVT_MAX_NODES);
+  if (S->n_recorders > PVT_MAX_RECORDERS) return fail("at most %d recorders are supported", PVT_MAX_RECORDERS);
+  if (S->root_id < 0 || S->root_id >= S->n_nodes) return fail("root_id out of range");
+  for (int i = 0; i < S->n_nodes; ++i) {
+    if (S->geom_type[i] < 0 || S->geom_type[i] > 2) return fail("node %d: unknown geometry tag %d", i, S->geom_type[i]);
+    if (S->comp_start[i] < 0 || S->comp_start[i] + S->comp_count[i] > S->n_components)
+      return fail("node %d: component range out of bounds", i);
+  }
+  for (int c = 0; c < S->n_components; ++c) {
+    if (S->comp_abs_n[c] < 1 || S->comp_abs_start[c] < 0 || S->comp_abs_start[c] + S->comp_abs_n[c] > S->n_abs_knots)
+      return fail("component %d: absorption table out of bounds", c);
+    if (S->comp_type[c] == PVT_COMP_LUMINOPHORE &&
+        (S->comp_ems_n[c] < 1 || S->comp_ems_start[c] < 0 || S->comp_ems_start[c] + S->comp_ems_n[c] > S->n_ems_knots))
+      return fail("component %d: emission table out of bounds", c);
+  }
+  for (int r = 0; r < S->n_recorders; ++r) {
+    if (S->rec_node[r] < 0 || S->rec_node[r] >= S->n_nodes) return fail("recorder %d: node out of range", r);
+    if (S->rec_hist_start[r] < 0 || S->rec_hist_start[r] + S->rec_hist_n[r] > S->n_hists)
+      return fail("recorder %d: histogram range out of bounds", r);
+  }
+  for (int h = 0; h < S->n_hists; ++h) {
+    const long long cells = (long long)S->hist_na[h] * (S->hist_prop_b[h] < 0 ? 1 : S->hist_nb[h]);
+    if (S->hist_offset[h] < 0 || S->hist_offset[h] + cells > S->total_bins) return fail("histogram %d: bins out of bounds", h);
+  }
+  return 0;
+}
+
+template <class K>
+static int occupancy(K kernel, size_t smem, int* blocks) {
+  if (smem > 48 * 1024)
+    PVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PVT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kernel, kTraceThreads, smem));
+  if (*blocks < 1) return fail("trace kernel cannot be resident with %zu bytes of shared memory", smem);
+  return 0;
+}
+
+extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context_t** out) {
+  if (!out) return fail("ctx out pointer is NULL");
+  *out = nullptr;
+  PVT_TRY(validate_scene(scene));
+  if (emit && emit->n_lights <= 0) return fail("emitter has no lights");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail("no CUDA device is usable (pvtrace_b200 has no CPU fallback)");
+  if (device < 0 || device >= n_dev) return fail("device %d out of range (have %d)", device, n_dev);
+  PVT_CUDA(cudaSetDevice(device));
+
+  pvt_context* c = new pvt_context();
+  c->device = device;
+  c->host_blob = pack_scene(*scene, emit);
+  memcpy(&c->hdr, c->host_blob.data(), sizeof(Header));
+  c->blob_words = c->hdr.total_words;
+  c->has_emitter = emit != nullptr;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete c; return fail("cudaGetDeviceProperties -> %s", cudaGetErrorString(e)); }
+  c->sm_count = prop.multiProcessorCount;
+  // the blob lives in shared memory when it leaves room for >= 2 CTAs per SM; otherwise it is read through L1
+  const size_t want = trace_smem_bytes(c->blob_words, c->R());
+  c->scene_in_smem = want <= (size_t)prop.sharedMemPerBlockOptin && want <= 100 * 1024;
+  c->smem_bytes = trace_smem_bytes(c->scene_in_smem ? c->blob_words : 0, c->R());
+
+  int rc = c->blob.reserve((size_t)c->blob_words);
+  c->tally_words = (size_t)10 * c->R() + c->B() + PVT_NSTATS + 1;
+  if (!rc) rc = c->tallies.reserve(c->tally_words);
+  if (!rc) rc = c->packed.reserve((size_t)10 * c->R() + c->B() + 1);
+  if (!rc && cudaMemcpy(c->blob.ptr, c->host_blob.data(), (size_t)c->blob_words * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = fail("scene upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!rc && cudaMemset(c->tallies.ptr, 0, c->tally_words * 8) != cudaSuccess)
+    rc = fail("tally reset failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!rc) rc = occupancy(trace_kernel<PhiloxStream, 2>, c->smem_bytes, &c->blocks_per_sm[0]);
+  if (!rc) rc = occupancy(trace_kernel<PhiloxStream, 8>, c->smem_bytes, &c->blocks_per_sm[1]);
+  if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 2>, c->smem_bytes, &c->blocks_per_sm[2]);
+  if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 8>, c->smem_bytes, &c->blocks_per_sm[3]);
+  if (!rc && c->smem_bytes > 48 * 1024 &&
+      cudaFuncSetAttribute(intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess)
+    rc = fail("cudaFuncSetAttribute(intersect_kernel) failed");
+  if (rc) {
+    pvt_context_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+extern "C" int pvt_context_destroy(pvt_context_t* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  c->blob.release(); c->tallies.release(); c->packed.release();
+  c->counts.release(); c->hit.release(); c->container.release(); c->adjacent.release(); c->component.release();
+  c->source.release(); c->kind.release(); c->position.release(); c->direction.release(); c->normal.release();
+  c->wavelength.release(); c->travelled.release(); c->duration.release();
+  delete c;
+  return 0;
+}
+
+extern "C" int pvt_context_reset(pvt_context_t* c, void* stream) {
+  if (!c) return fail("ctx is NULL");
+  PVT_CUDA(cudaSetDevice(c->device));
+  PVT_CUDA(cudaMemsetAsync(c->tallies.ptr, 0, c->tally_words * 8, (cudaStream_t)stream));
+  c->launches = 0;
+  return 0;
+}
+
+static int prepare_log(pvt_context* c, const pvt_params_t* P, cudaStream_t st) {
+  c->log_rows = 0;
+  c->log_rays = 0;
+  if (P->record_every <= 0) return 0;
+  const long long rays = (P->n + P->record_every - 1) / P->record_every;
+  const long long rows = rays * (long long)P->max_events;
+  PVT_TRY(c->counts.reserve((size_t)rays));
+  PVT_TRY(c->kind.reserve((size_t)rows));
+  PVT_TRY(c->hit.reserve((size_t)rows));
+  PVT_TRY(c->container.reserve((size_t)rows));
+  PVT_TRY(c->adjacent.reserve((size_t)rows));
+  PVT_TRY(c->component.reserve((size_t)rows));
+  PVT_TRY(c->source.reserve((size_t)rows));
+  PVT_TRY(c->position.reserve((size_t)rows * 3));
+  PVT_TRY(c->direction.reserve((size_t)rows * 3));
+  PVT_TRY(c->normal.reserve((size_t)rows * 3));
+  PVT_TRY(c->wavelength.reserve((size_t)rows));
+  PVT_TRY(c->travelled.reserve((size_t)rows));
+  PVT_TRY(c->duration.reserve((size_t)rows));
+  // initial values of the reference's log arrays (_kernel.pyx:1035-1047): ids -1, everything else 0
+  PVT_CUDA(cudaMemsetAsync(c->counts.ptr, 0, (size_t)rays * 4, st));
+  PVT_CUDA(cudaMemsetAsync(c->kind.ptr, 0, (size_t)rows, st));
+  PVT_CUDA(cudaMemsetAsync(c->hit.ptr, 0xFF, (size_t)rows * 4, st));
+  PVT_CUDA(cudaMemsetAsync(c->container.ptr, 0xFF, (size_t)rows * 4, st));
+  PVT_CUDA(cudaMemsetAsync(c->adjacent.ptr, 0xFF, (size_t)rows * 4, st));
+  PVT_CUDA(cudaMemsetAsync(c->component.ptr, 0xFF, (size_t)rows * 4, st));
+  PVT_CUDA(cudaMemsetAsync(c->source.ptr, 0xFF, (size_t)rows * 4, st));
+  PVT_CUDA(cudaMemsetAsync(c->position.ptr, 0, (size_t)rows * 24, st));
+  PVT_CUDA(cudaMemsetAsync(c->direction.ptr, 0, (size_t)rows * 24, st));
+  PVT_CUDA(cudaMemsetAsync(c->normal.ptr, 0, (size_t)rows * 24, st));
+  PVT_CUDA(cudaMemsetAsync(c->wavelength.ptr, 0, (size_t)rows * 8, st));
+  PVT_CUDA(cudaMemsetAsync(c->travelled.ptr, 0, (size_t)rows * 8, st));
+  PVT_CUDA(cudaMemsetAsync(c->duration.ptr, 0, (size_t)rows * 8, st));
+  c->log_rows = rows;
+  c->log_rays = rays;
+  return 0;
+}
+
+static int check_params(const pvt_params_t* P) {
+  if (!P) return fail("params is NULL");
+  if (P->n < 0) return fail("n must be >= 0");
+  if (P->emit_method < 0 || P->emit_method > 2) return fail("emit_method must be 0 (kT), 1 (redshift) or 2 (full)");
+  if (P->rng_mode != PVT_RNG_PHILOX && P->rng_mode != PVT_RNG_XOSHIRO) return fail("unknown rng_mode %d", P->rng_mode);
+  if (P->record_every < 0) return fail("record_every must be >= 0");
+  if (P->record_every > 0 && P->max_events < 2) return fail("max_events must be >= 2 when rays are recorded");
+  return 0;
+}
+
+extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
+                                const pvt_params_t* P, void* stream) {
+  if (!c) return fail("ctx is NULL");
+  PVT_TRY(check_params(P));
+  const bool have_rays = d_pos && d_dir && d_wl;
+  if (!have_rays && !c->has_emitter) return fail("no ray arrays given and the context has no emitter");
+  PVT_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  PVT_TRY(prepare_log(c, P, st));
+  if (P->n == 0) return 0;
+  PVT_CUDA(cudaMemsetAsync(c->d_work(), 0, 8, st));
+
+  TraceArgs a;
+  a.blob = c->blob.ptr; a.blob_words = c->blob_words; a.scene_in_smem = c->scene_in_smem;
+  a.pos = have_rays ? d_pos : nullptr; a.dir = have_rays ? d_dir : nullptr; a.wl = have_rays ? d_wl : nullptr;
+  a.n = P->n; a.first_index = P->first_index; a.record_every = P->record_every; a.seed = P->seed;
+  a.sp.maxsteps = P->maxsteps; a.sp.max_events = P->max_events; a.sp.emit_method = P->emit_method;
+  a.work_counter = c->d_work();
+  a.g_distinct = c->d_distinct(); a.g_cross = c->d_cross(); a.g_sums = c->d_sums(); a.g_bins = c->d_bins();
+  a.g_stats = c->d_stats();
+  a.log = LogColumns{c->counts.ptr, c->kind.ptr, c->hit.ptr, c->container.ptr, c->adjacent.ptr, c->component.ptr,
+                     c->source.ptr, c->position.ptr, c->direction.ptr, c->normal.ptr, c->wavelength.ptr,
+                     c->travelled.ptr, c->duration.ptr};
+
+  const int wide = c->R() > 64;
+  const int which = (P->rng_mode == PVT_RNG_XOSHIRO ? 2 : 0) + wide;
+  long long want_blocks = (P->n + kTraceThreads - 1) / kTraceThreads;
+  const long long resident = (long long)c->sm_count * c->blocks_per_sm[which];
+  const int grid = (int)(want_blocks < resident ? want_blocks : resident);
+  switch (which) {
+    case 0: trace_kernel<PhiloxStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+    case 1: trace_kernel<PhiloxStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+    case 2: trace_kernel<XoshiroStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+    default: trace_kernel<XoshiroStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+  }
+  PVT_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return 0;
+}
+
+template <class T>
+static int fetch(T* host, const T* dev, size_t count, cudaStream_t st) {
+  if (!host || count == 0) return 0;
+  PVT_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+extern "C" int pvt_context_read(pvt_context_t* c, pvt_out_t* out, void* stream) {
+  if (!c || !out) return fail("ctx/out is NULL");
+  PVT_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = c->R(), B = c->B();
+  // int64 <- u64 is a reinterpretation; counts never approach 2^63
+  PVT_TRY(fetch(reinterpret_cast<u64*>(out->rec_distinct), c->d_distinct(), (size_t)R, st));
+  PVT_TRY(fetch(reinterpret_cast<u64*>(out->rec_crossings), c->d_cross(), (size_t)R, st));
+  PVT_TRY(fetch(out->rec_sums, c->d_sums(), (size_t)8 * R, st));
+  PVT_TRY(fetch(reinterpret_cast<u64*>(out->rec_bins), c->d_bins(), (size_t)B, st));
+  if (out->stats) PVT_TRY(fetch(reinterpret_cast<u64*>(out->stats), c->d_stats(), (size_t)PVT_NSTATS, st));
+  if (c->log_rows > 0 && out->kind) {
+    const size_t rows = (size_t)c->log_rows;
+    PVT_TRY(fetch(out->counts, c->counts.ptr, (size_t)c->log_rays, st));
+    PVT_TRY(fetch(out->kind, c->kind.ptr, rows, st));
+    PVT_TRY(fetch(out->hit, c->hit.ptr, rows, st));
+    PVT_TRY(fetch(out->container, c->container.ptr, rows, st));
+    PVT_TRY(fetch(out->adjacent, c->adjacent.ptr, rows, st));
+    PVT_TRY(fetch(out->component, c->component.ptr, rows, st));
+    PVT_TRY(fetch(out->source, c->source.ptr, rows, st));
+    PVT_TRY(fetch(out->position, c->position.ptr, rows * 3, st));
+    PVT_TRY(fetch(out->direction, c->direction.ptr, rows * 3, st));
+    PVT_TRY(fetch(out->normal, c->normal.ptr, rows * 3, st));
+    PVT_TRY(fetch(out->wavelength, c->wavelength.ptr, rows, st));
+    PVT_TRY(fetch(out->travelled, c->travelled.ptr, rows, st));
+    PVT_TRY(fetch(out->duration, c->duration.ptr, rows, st));
+  }
+  PVT_CUDA(cudaStreamSynchronize(st));
+  if (out->stats) out->stats[PVT_STAT_LAUNCHES] = c->launches;
+  return 0;
+}
+
+extern "C" int pvt_context_pack_tallies(pvt_context_t* c, double** d_packed, int64_t* n_packed, void* stream) {
+  if (!c || !d_packed || !n_packed) return fail("NULL argument");
+  PVT_CUDA(cudaSetDevice(c->device));
+  const int R = c->R(), B = c->B();
+  const int total = 10 * R + B;
+  if (total > 0) {
+    pack_tallies_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->d_distinct(), 2 * R, c->d_sums(), 8 * R,
+                                                                               c->d_bins(), B, c->packed.ptr);
+    PVT_CUDA(cudaGetLastError());
+  }
+  *d_packed = c->packed.ptr;
+  *n_packed = total;
+  return 0;
+}
+
+extern "C" int pvt_context_unpack_tallies(pvt_context_t* c, void* stream) {
+  if (!c) return fail("ctx is NULL");
+  PVT_CUDA(cudaSetDevice(c->device));
+  const int R = c->R(), B = c->B();
+  const int total = 10 * R + B;
+  if (total > 0) {
+    unpack_tallies_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(c->d_distinct(), 2 * R, c->d_sums(), 8 * R,
+                                                                                 c->d_bins(), B, c->packed.ptr);
+    PVT_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+static int grid_for(long long n, int sm_count) {
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+extern "C" int pvt_emit_device(pvt_context_t* c, double* d_pos, double* d_dir, double* d_wl, int64_t n, int64_t first_index,
+                               uint64_t seed, void* stream) {
+  if (!c) return fail("ctx is NULL");
+  if (!c->has_emitter) return fail("the context has no emitter");
+  if (n <= 0) return 0;
+  PVT_CUDA(cudaSetDevice(c->device));
+  emit_kernel<<<grid_for(n, c->sm_count), 256, 0, (cudaStream_t)stream>>>(c->blob.ptr, d_pos, d_dir, d_wl, n, first_index, seed);
+  PVT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int pvt_intersect_device(pvt_context_t* c, const double* d_pos, const double* d_dir, int64_t n, double* d_t0,
+                                    int32_t* d_hit, int32_t* d_container, int32_t* d_adjacent, void* stream) {
+  if (!c) return fail("ctx is NULL");
+  if (n <= 0) return 0;
+  PVT_CUDA(cudaSetDevice(c->device));
+  intersect_kernel<<<grid_for(n, c->sm_count), 256, c->smem_bytes, (cudaStream_t)stream>>>(
+      c->blob.ptr, c->blob_words, c->scene_in_smem, d_pos, d_dir, n, d_t0, d_hit, d_container, d_adjacent);
+  PVT_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-buffer entry points
+
+namespace {
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  int start() {
+    PVT_CUDA(cudaEventCreate(&a));
+    PVT_CUDA(cudaEventCreate(&b));
+    PVT_CUDA(cudaEventRecord(a, 0));
+    return 0;
+  }
+  int stop(double* seconds) {
+    PVT_CUDA(cudaEventRecord(b, 0));
+    PVT_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    PVT_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (seconds) *seconds = ms * 1e-3;
+    return 0;
+  }
+  ~Timer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
+// One cached context per process: bundles of the same scene (engine.simulate_stream, repeated simulate calls)
+// reuse the uploaded blob and every device buffer.
+std::mutex g_cache_mutex;
+pvt_context* g_cached = nullptr;
+DeviceBuffer<double> g_rays;  // staging for host rays: [pos 3n | dir 3n | wl n]
+int g_rays_device = -1;
+
+int acquire_context(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context** out) {
+  PVT_TRY(validate_scene(scene));
+  std::vector<double> blob = pack_scene(*scene, emit);
+  if (g_cached && g_cached->device == device && g_cached->host_blob.size() == blob.size() &&
+      memcmp(g_cached->host_blob.data(), blob.data(), blob.size() * 8) == 0 && g_cached->has_emitter == (emit != nullptr)) {
+    *out = g_cached;
+    return 0;
+  }
+  if (g_cached) { pvt_context_destroy(g_cached); g_cached = nullptr; }
+  PVT_TRY(pvt_context_create(scene, emit, device, &g_cached));
+  *out = g_cached;
+  return 0;
+}
+}  // namespace
+
+extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, const double* positions,
+                                const double* directions, const double* wavelengths, const pvt_params_t* params,
+                                pvt_out_t* out, double* elapsed_s) {
+  PVT_TRY(check_params(params));
+  if (!out) return fail("out is NULL");
+  const bool have_rays = positions && directions && wavelengths;
+  if (!have_rays && !emit) return fail("either ray arrays or an emitter are required");
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  pvt_context* c = nullptr;
+  PVT_TRY(acquire_context(scene, emit, params->device, &c));
+  PVT_CUDA(cudaSetDevice(c->device));
+  Timer timer;
+  PVT_TRY(timer.start());
+  const size_t n = (size_t)params->n;
+  const double *d_pos = nullptr, *d_dir = nullptr, *d_wl = nullptr;
+  if (have_rays && n > 0) {
+    if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
+    PVT_TRY(g_rays.reserve(7 * n));
+    PVT_CUDA(cudaMemcpyAsync(g_rays.ptr, positions, 24 * n, cudaMemcpyHostToDevice, 0));
+    PVT_CUDA(cudaMemcpyAsync(g_rays.ptr + 3 * n, directions, 24 * n, cudaMemcpyHostToDevice, 0));
+    PVT_CUDA(cudaMemcpyAsync(g_rays.ptr + 6 * n, wavelengths, 8 * n, cudaMemcpyHostToDevice, 0));
+    d_pos = g_rays.ptr; d_dir = g_rays.ptr + 3 * n; d_wl = g_rays.ptr + 6 * n;
+  }
+  PVT_TRY(pvt_context_reset(c, 0));
+  PVT_TRY(pvt_trace_device(c, d_pos, d_dir, d_wl, params, 0));
+  PVT_TRY(pvt_context_read(c, out, 0));
+  PVT_TRY(timer.stop(elapsed_s));
+  return 0;
+}
+
+extern "C" int pvt_emit_bundle(const pvt_emit_t* emit, double* positions, double* directions, double* wavelengths, int64_t n,
+                               int64_t first_index, uint64_t seed, int device) {
+  if (!emit || emit->n_lights <= 0) return fail("emitter has no lights");
+  if (n <= 0) return 0;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail("no CUDA device is usable (pvtrace_b200 has no CPU fallback)");
+  PVT_CUDA(cudaSetDevice(device));
+  // an emitter-only blob: a scene with no nodes
+  pvt_scene_t empty;
+  memset(&empty, 0, sizeof(empty));
+  std::vector<double> blob = pack_scene(empty, emit);
+  DeviceBuffer<double> d_blob, d_rays;
+  int rc = d_blob.reserve(blob.size());
+  if (!rc) rc = d_rays.reserve((size_t)7 * n);
+  if (!rc && cudaMemcpy(d_blob.ptr, blob.data(), blob.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+    rc = fail("emitter upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+  if (!rc) {
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    emit_kernel<<<grid_for(n, prop.multiProcessorCount), 256>>>(d_blob.ptr, d_rays.ptr, d_rays.ptr + 3 * n, d_rays.ptr + 6 * n, n,
+                                                              first_index, seed);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(positions, d_rays.ptr, 24 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(directions, d_rays.ptr + 3 * n, 24 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(wavelengths, d_rays.ptr + 6 * n, 8 * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = fail("emit failed: %s", cudaGetErrorString(e));
+  }
+  d_blob.release();
+  d_rays.release();
+  return rc;
+}
+
+extern "C" int pvt_intersect_bundle(const pvt_scene_t* scene, const double* positions, const double* directions, int64_t n,
+                                    double* t0, int32_t* hit, int32_t* container, int32_t* adjacent, int device,
+                                    double* elapsed_s) {
+  if (n < 0) return fail("n must be >= 0");
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  pvt_context* c = nullptr;
+  PVT_TRY(acquire_context(scene, nullptr, device, &c));
+  PVT_CUDA(cudaSetDevice(c->device));
+  if (n == 0) return 0;
+  DeviceBuffer<double> in, d_t0;
+  DeviceBuffer<int32_t> ids;
+  int rc = in.reserve((size_t)6 * n);
+  if (!rc) rc = d_t0.reserve((size_t)n);
+  if (!rc) rc = ids.reserve((size_t)3 * n);
+  Timer timer;
+  if (!rc) rc = timer.start();
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(in.ptr, positions, 24 * (size_t)n, cudaMemcpyHostToDevice, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in.ptr + 3 * n, directions, 24 * (size_t)n, cudaMemcpyHostToDevice, 0);
+    if (e != cudaSuccess) rc = fail("ray upload failed: %s", cudaGetErrorString(e));
+  }
+  if (!rc) rc = pvt_intersect_device(c, in.ptr, in.ptr + 3 * n, n, d_t0.ptr, ids.ptr, ids.ptr + n, ids.ptr + 2 * n, 0);
+  if (!rc) {
+    cudaError_t e = cudaMemcpyAsync(t0, d_t0.ptr, 8 * (size_t)n, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hit, ids.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(container, ids.ptr + n, 4 * (size_t)n, cudaMemcpyDeviceToHost, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(adjacent, ids.ptr + 2 * n, 4 * (size_t)n, cudaMemcpyDeviceToHost, 0);
+    if (e != cudaSuccess) rc = fail("result download failed: %s", cudaGetErrorString(e));
+  }
+  if (!rc) rc = timer.stop(elapsed_s);
+  in.release(); d_t0.release(); ids.release();
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Library queries
+
+extern "C" int pvt_version(void) { return PVT_VERSION; }
+extern "C" int pvt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" const char* pvt_last_error(void) { return error_buffer(); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Known-answer helpers: upload, one launch, download.
+
+namespace {
+struct Scratch {
+  std::vector<void*> ptrs;
+  ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+  template <class T>
+  T* up(const T* host, size_t count) {
+    T* d = nullptr;
+    if (cudaMalloc((void**)&d, (count ? count : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    ptrs.push_back(d);
+    if (host && count && cudaMemcpy(d, host, count * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    return d;
+  }
+};
+int begin_test(int device) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail("no CUDA device is usable (pvtrace_b200 has no CPU fallback)");
+  PVT_CUDA(cudaSetDevice(device));
+  return 0;
+}
+template <class T>
+int finish_test(T* host, const T* dev, size_t count) {
+  PVT_CUDA(cudaGetLastError());
+  PVT_CUDA(cudaMemcpy(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost));
+  return 0;
+}
+inline int blocks(int64_t n) { return (int)((n + 255) / 256); }
+}  // namespace
+
+#define PVT_NEED(p) if (!(p)) return fail("device allocation/upload failed")
+
+extern "C" int pvt_test_fresnel_reflectivity(int64_t n, const double* angle, const double* n1, const double* n2, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  Scratch s;
+  double *a = s.up(angle, n), *b = s.up(n1, n), *c = s.up(n2, n), *o = s.up<double>(nullptr, n);
+  PVT_NEED(a && b && c && o);
+  test_fresnel_kernel<<<blocks(n), 256>>>(n, a, b, c, o);
+  return finish_test(out, o, n);
+}
+extern "C" int pvt_test_specular_reflect(int64_t n, const double* d, const double* nrm, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  Scratch s;
+  double *a = s.up(d, 3 * n), *b = s.up(nrm, 3 * n), *o = s.up<double>(nullptr, 3 * n);
+  PVT_NEED(a && b && o);
+  test_reflect_kernel<<<blocks(n), 256>>>(n, a, b, o);
+  return finish_test(out, o, 3 * n);
+}
+extern "C" int pvt_test_fresnel_refract(int64_t n, const double* d, const double* nrm, const double* n1, const double* n2, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  Scratch s;
+  double *a = s.up(d, 3 * n), *b = s.up(nrm, 3 * n), *c = s.up(n1, n), *e = s.up(n2, n), *o = s.up<double>(nullptr, 3 * n);
+  PVT_NEED(a && b && c && e && o);
+  test_refract_kernel<<<blocks(n), 256>>>(n, a, b, c, e, o);
+  return finish_test(out, o, 3 * n);
+}
+extern "C" int pvt_test_intersect(int64_t n, const int32_t* geom_type, const double* params, const double* o, const double* d,
+                                  int32_t* nhit, double* ts, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  Scratch s;
+  int32_t* g = s.up(geom_type, n);
+  double *p = s.up(params, 4 * n), *oo = s.up(o, 3 * n), *dd = s.up(d, 3 * n), *t = s.up<double>(nullptr, 4 * n);
+  int32_t* k = s.up<int32_t>(nullptr, n);
+  PVT_NEED(g && p && oo && dd && t && k);
+  test_intersect_kernel<<<blocks(n), 256>>>(n, g, p, oo, dd, k, t);
+  PVT_TRY(finish_test(nhit, k, n));
+  return finish_test(ts, t, 4 * n);
+}
+extern "C" int pvt_test_local_normal(int64_t n, const int32_t* geom_type, const double* params, const double* p, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  Scratch s;
+  int32_t* g = s.up(geom_type, n);
+  double *q = s.up(params, 4 * n), *pp = s.up(p, 3 * n), *o = s.up<double>(nullptr, 3 * n);
+  PVT_NEED(g && q && pp && o);
+  test_normal_kernel<<<blocks(n), 256>>>(n, g, q, pp, o);
+  return finish_test(out, o, 3 * n);
+}
+extern "C" int pvt_test_interp(int64_t n, const double* x, int32_t m, const double* xs, const double* ys, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  if (m < 1) return fail("table needs at least one knot");
+  Scratch s;
+  double *a = s.up(x, n), *b = s.up(xs, m), *c = s.up(ys, m), *o = s.up<double>(nullptr, n);
+  PVT_NEED(a && b && c && o);
+  // same host decision as the scene packer: uniform grids take the guessed-bracket path
+  test_interp_kernel<<<blocks(n), 256>>>(n, a, m, b, c, uniform_inv_dx(xs, m), o);
+  return finish_test(out, o, n);
+}
+extern "C" int pvt_test_rng_uniform(int64_t n_rays, int32_t n_draws, uint64_t seed, int64_t first_index, int32_t rng_mode, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n_rays <= 0 || n_draws <= 0) return 0;
+  Scratch s;
+  double* o = s.up<double>(nullptr, (size_t)n_rays * n_draws);
+  PVT_NEED(o);
+  if (rng_mode == PVT_RNG_XOSHIRO) test_rng_kernel<XoshiroStream><<<blocks(n_rays), 256>>>(n_rays, n_draws, seed, first_index, o);
+  else test_rng_kernel<PhiloxStream><<<blocks(n_rays), 256>>>(n_rays, n_draws, seed, first_index, o);
+  return finish_test(out, o, (size_t)n_rays * n_draws);
+}
+extern "C" int pvt_test_sample_phase(int64_t n, int32_t phase_type, double phase_param, uint64_t seed, int32_t rng_mode, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  Scratch s;
+  double* o = s.up<double>(nullptr, 3 * n);
+  PVT_NEED(o);
+  if (rng_mode == PVT_RNG_XOSHIRO) test_phase_kernel<XoshiroStream><<<blocks(n), 256>>>(n, phase_type, phase_param, seed, o);
+  else test_phase_kernel<PhiloxStream><<<blocks(n), 256>>>(n, phase_type, phase_param, seed, o);
+  return finish_test(out, o, 3 * n);
+}

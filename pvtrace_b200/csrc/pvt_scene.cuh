@@ -1,0 +1,190 @@
+// pvt_scene.cuh -- the device-resident scene: ONE contiguous blob of 8-byte words that every CTA stages into
+// shared memory with a single bulk async copy (cp.async.bulk, the TMA engine's 1-D path) before tracing.
+//
+// Host side: pack_scene() turns the flat tables of include/pvtrace_b200.h (pvt_scene_t / pvt_emit_t, themselves
+// the reference's CompiledScene contract, pvtrace/engine/compiler.py:57-204) into the blob.  Per-entity records
+// (node / component / recorder / histogram / facet / light) are arrays-of-structs because every lane of a warp
+// reads the SAME record at the same time (shared-memory broadcast); spectra stay as plain arrays.
+//
+// Word layout (all offsets in 8-byte words from the start of the blob):
+//   [0, kHeaderWords)  header: int32 pairs, see Header
+//   nodes       n_nodes      x kNodeWords
+//   components  n_components x kCompWords
+//   abs_x, abs_y, ems_x, ems_cdf  (spectra knots)
+//   recorders   n_recorders  x kRecWords
+//   hists       n_hists      x kHistWords
+//   facets      n_facets     x kFacetWords
+//   lights      n_lights     x kLightWords, wl_x, wl_cdf
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/pvtrace_b200.h"
+
+namespace pvt {
+
+struct Header {
+  int32_t n_nodes, root_id, n_components, n_recorders, n_hists, total_bins, n_facets, n_lights;
+  int32_t off_nodes, off_comps, off_abs_x, off_abs_y, off_ems_x, off_ems_cdf, off_recs, off_hists;
+  int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, pad0, pad1, pad2;
+};
+constexpr int kHeaderWords = sizeof(Header) / 8;
+static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
+
+// node record: w2l rows 0-2 (12) | l2w rows 0-2 (12) | params (4) | n (1) | ints: geom,surf | comp_start,comp_count | facet_start,facet_count
+constexpr int kNodeW2L = 0, kNodeL2W = 12, kNodeParams = 24, kNodeIndex = 28, kNodeInts = 29, kNodeWords = 32;
+// component record: qy, tau_rad, tau_nr, phase_param | ints: type,phase_type | abs_start,abs_n | ems_start,ems_n |
+// abs_inv_dx, ems_inv_dx (1/spacing of the x grid when it is uniform enough for interp_hinted, else 0) | pad
+constexpr int kCompQy = 0, kCompTauRad = 1, kCompTauNr = 2, kCompPhaseParam = 3, kCompInts = 4, kCompAbsInvDx = 7,
+              kCompEmsInvDx = 8, kCompWords = 10;
+// recorder record: facet xyz, atol | ints: node,event | has_facet,hist_start | hist_n,pad | pad
+constexpr int kRecFacet = 0, kRecAtol = 3, kRecInts = 4, kRecWords = 8;
+// histogram record: lo_a, hi_a, lo_b, hi_b | ints: prop_a,prop_b | na,nb | offset,pad | pad
+constexpr int kHistLoA = 0, kHistHiA = 1, kHistLoB = 2, kHistHiB = 3, kHistInts = 4, kHistWords = 8;
+// facet record: normal xyz, atol, reflectivity | ints: flags,pad | pad pad
+constexpr int kFacetNormal = 0, kFacetAtol = 3, kFacetRefl = 4, kFacetInts = 5, kFacetWords = 8;
+// light record: l2w rows 0-2 (12) | pos_param (3) | dir_param | wl_param | ints: pos_kind,dir_kind | wl_kind,wl_start | wl_n,pad
+constexpr int kLightL2W = 0, kLightPos = 12, kLightDir = 15, kLightWl = 16, kLightInts = 17, kLightWords = 20;
+
+// 1/dx when xs[0..n) is an (almost) uniform ascending grid: every knot within 0.45 dx of xs[0] + i dx, so a
+// guessed bracket is at most one knot away from the true one.  0 otherwise.
+inline double uniform_inv_dx(const double* xs, int n) {
+  if (n < 3) return 0.0;
+  const double dx = (xs[n - 1] - xs[0]) / (n - 1);
+  if (!(dx > 0.0)) return 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double dev = xs[i] - (xs[0] + i * dx);
+    if (dev > 0.45 * dx || dev < -0.45 * dx) return 0.0;
+  }
+  return 1.0 / dx;
+}
+
+inline void put_ints(std::vector<double>& blob, size_t word, int32_t a, int32_t b) {
+  int32_t pair[2] = {a, b};
+  memcpy(&blob[word], pair, 8);
+}
+
+// Returns the blob; its size is a multiple of 2 words (16 bytes).
+inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E) {
+  Header h;
+  memset(&h, 0, sizeof(h));
+  h.n_nodes = S.n_nodes; h.root_id = S.root_id; h.n_components = S.n_components; h.n_recorders = S.n_recorders;
+  h.n_hists = S.n_hists; h.total_bins = S.total_bins; h.n_facets = S.facet_count ? S.n_facets : 0;
+  h.n_lights = E ? E->n_lights : 0;
+  int32_t w = kHeaderWords;
+  h.off_nodes = w;   w += S.n_nodes * kNodeWords;
+  h.off_comps = w;   w += S.n_components * kCompWords;
+  h.off_abs_x = w;   w += S.n_abs_knots;
+  h.off_abs_y = w;   w += S.n_abs_knots;
+  h.off_ems_x = w;   w += S.n_ems_knots;
+  h.off_ems_cdf = w; w += S.n_ems_knots;
+  h.off_recs = w;    w += S.n_recorders * kRecWords;
+  h.off_hists = w;   w += S.n_hists * kHistWords;
+  h.off_facets = w;  w += h.n_facets * kFacetWords;
+  h.off_lights = w;  w += h.n_lights * kLightWords;
+  h.off_wl_x = w;    w += E ? E->n_wl_knots : 0;
+  h.off_wl_cdf = w;  w += E ? E->n_wl_knots : 0;
+  w = (w + 1) & ~1;
+  h.total_words = w;
+
+  std::vector<double> blob((size_t)w, 0.0);
+  memcpy(blob.data(), &h, sizeof(h));
+  for (int i = 0; i < S.n_nodes; ++i) {
+    double* r = &blob[h.off_nodes + (size_t)i * kNodeWords];
+    memcpy(r + kNodeW2L, S.world_to_local + 16 * i, 12 * sizeof(double));
+    memcpy(r + kNodeL2W, S.local_to_world + 16 * i, 12 * sizeof(double));
+    memcpy(r + kNodeParams, S.geom_params + 4 * i, 4 * sizeof(double));
+    r[kNodeIndex] = S.refractive_index[i];
+    const size_t iw = h.off_nodes + (size_t)i * kNodeWords + kNodeInts;
+    put_ints(blob, iw, S.geom_type[i], S.surface_type[i]);
+    put_ints(blob, iw + 1, S.comp_start[i], S.comp_count[i]);
+    put_ints(blob, iw + 2, h.n_facets ? S.facet_start[i] : 0, h.n_facets ? S.facet_count[i] : 0);
+  }
+  for (int c = 0; c < S.n_components; ++c) {
+    double* r = &blob[h.off_comps + (size_t)c * kCompWords];
+    r[kCompQy] = S.comp_qy[c]; r[kCompTauRad] = S.comp_tau_rad[c]; r[kCompTauNr] = S.comp_tau_nr[c];
+    r[kCompPhaseParam] = S.comp_phase_param[c];
+    const size_t iw = h.off_comps + (size_t)c * kCompWords + kCompInts;
+    put_ints(blob, iw, S.comp_type[c], S.comp_phase_type[c]);
+    put_ints(blob, iw + 1, S.comp_abs_start[c], S.comp_abs_n[c]);
+    put_ints(blob, iw + 2, S.comp_ems_start[c], S.comp_ems_n[c]);
+    r[kCompAbsInvDx] = uniform_inv_dx(S.abs_x + S.comp_abs_start[c], S.comp_abs_n[c]);
+    r[kCompEmsInvDx] = S.comp_ems_n[c] > 0 ? uniform_inv_dx(S.ems_x + S.comp_ems_start[c], S.comp_ems_n[c]) : 0.0;
+  }
+  if (S.n_abs_knots) {
+    memcpy(&blob[h.off_abs_x], S.abs_x, S.n_abs_knots * sizeof(double));
+    memcpy(&blob[h.off_abs_y], S.abs_y, S.n_abs_knots * sizeof(double));
+  }
+  if (S.n_ems_knots) {
+    memcpy(&blob[h.off_ems_x], S.ems_x, S.n_ems_knots * sizeof(double));
+    memcpy(&blob[h.off_ems_cdf], S.ems_cdf, S.n_ems_knots * sizeof(double));
+  }
+  for (int r = 0; r < S.n_recorders; ++r) {
+    double* q = &blob[h.off_recs + (size_t)r * kRecWords];
+    q[0] = S.rec_facet[3 * r]; q[1] = S.rec_facet[3 * r + 1]; q[2] = S.rec_facet[3 * r + 2];
+    q[kRecAtol] = S.rec_atol[r];
+    const size_t iw = h.off_recs + (size_t)r * kRecWords + kRecInts;
+    put_ints(blob, iw, S.rec_node[r], S.rec_event[r]);
+    put_ints(blob, iw + 1, S.rec_has_facet[r], S.rec_hist_start[r]);
+    put_ints(blob, iw + 2, S.rec_hist_n[r], 0);
+  }
+  for (int k = 0; k < S.n_hists; ++k) {
+    double* q = &blob[h.off_hists + (size_t)k * kHistWords];
+    q[kHistLoA] = S.hist_lo_a[k]; q[kHistHiA] = S.hist_hi_a[k]; q[kHistLoB] = S.hist_lo_b[k]; q[kHistHiB] = S.hist_hi_b[k];
+    const size_t iw = h.off_hists + (size_t)k * kHistWords + kHistInts;
+    put_ints(blob, iw, S.hist_prop_a[k], S.hist_prop_b[k]);
+    put_ints(blob, iw + 1, S.hist_na[k], S.hist_nb[k]);
+    put_ints(blob, iw + 2, S.hist_offset[k], 0);
+  }
+  for (int f = 0; f < h.n_facets; ++f) {
+    double* q = &blob[h.off_facets + (size_t)f * kFacetWords];
+    q[0] = S.facet_normal[3 * f]; q[1] = S.facet_normal[3 * f + 1]; q[2] = S.facet_normal[3 * f + 2];
+    q[kFacetAtol] = S.facet_atol[f]; q[kFacetRefl] = S.facet_reflectivity[f];
+    put_ints(blob, h.off_facets + (size_t)f * kFacetWords + kFacetInts, S.facet_flags[f], 0);
+  }
+  for (int l = 0; l < h.n_lights; ++l) {
+    double* q = &blob[h.off_lights + (size_t)l * kLightWords];
+    memcpy(q + kLightL2W, E->light_to_world + 16 * l, 12 * sizeof(double));
+    q[kLightPos] = E->pos_param[3 * l]; q[kLightPos + 1] = E->pos_param[3 * l + 1]; q[kLightPos + 2] = E->pos_param[3 * l + 2];
+    q[kLightDir] = E->dir_param[l]; q[kLightWl] = E->wl_param[l];
+    const size_t iw = h.off_lights + (size_t)l * kLightWords + kLightInts;
+    put_ints(blob, iw, E->pos_kind[l], E->dir_kind[l]);
+    put_ints(blob, iw + 1, E->wl_kind[l], E->wl_start[l]);
+    put_ints(blob, iw + 2, E->wl_n[l], 0);
+  }
+  if (E && E->n_wl_knots) {
+    memcpy(&blob[h.off_wl_x], E->wl_x, E->n_wl_knots * sizeof(double));
+    memcpy(&blob[h.off_wl_cdf], E->wl_cdf, E->n_wl_knots * sizeof(double));
+  }
+  return blob;
+}
+
+#ifdef __CUDACC__
+// Read-only typed view over a blob held in shared (or, for oversized scenes, global) memory.
+struct SceneView {
+  const double* w;  // blob words
+  __device__ __forceinline__ const Header& hdr() const { return *reinterpret_cast<const Header*>(w); }
+  __device__ __forceinline__ int ival(int word, int half) const { return reinterpret_cast<const int32_t*>(w)[2 * word + half]; }
+  __device__ __forceinline__ const double* node(int i) const { return w + hdr().off_nodes + i * kNodeWords; }
+  __device__ __forceinline__ int node_int(int i, int k) const { return ival(hdr().off_nodes + i * kNodeWords + kNodeInts + (k >> 1), k & 1); }
+  __device__ __forceinline__ const double* comp(int c) const { return w + hdr().off_comps + c * kCompWords; }
+  __device__ __forceinline__ int comp_int(int c, int k) const { return ival(hdr().off_comps + c * kCompWords + kCompInts + (k >> 1), k & 1); }
+  __device__ __forceinline__ const double* rec(int r) const { return w + hdr().off_recs + r * kRecWords; }
+  __device__ __forceinline__ int rec_int(int r, int k) const { return ival(hdr().off_recs + r * kRecWords + kRecInts + (k >> 1), k & 1); }
+  __device__ __forceinline__ const double* hist(int h) const { return w + hdr().off_hists + h * kHistWords; }
+  __device__ __forceinline__ int hist_int(int h, int k) const { return ival(hdr().off_hists + h * kHistWords + kHistInts + (k >> 1), k & 1); }
+  __device__ __forceinline__ const double* facet(int f) const { return w + hdr().off_facets + f * kFacetWords; }
+  __device__ __forceinline__ int facet_flags(int f) const { return ival(hdr().off_facets + f * kFacetWords + kFacetInts, 0); }
+  __device__ __forceinline__ const double* light(int l) const { return w + hdr().off_lights + l * kLightWords; }
+  __device__ __forceinline__ int light_int(int l, int k) const { return ival(hdr().off_lights + l * kLightWords + kLightInts + (k >> 1), k & 1); }
+};
+// int slots of the records
+enum { NI_GEOM = 0, NI_SURF = 1, NI_COMP_START = 2, NI_COMP_COUNT = 3, NI_FACET_START = 4, NI_FACET_COUNT = 5 };
+enum { CI_TYPE = 0, CI_PHASE = 1, CI_ABS_START = 2, CI_ABS_N = 3, CI_EMS_START = 4, CI_EMS_N = 5 };
+enum { RI_NODE = 0, RI_EVENT = 1, RI_HAS_FACET = 2, RI_HIST_START = 3, RI_HIST_N = 4 };
+enum { HI_PROP_A = 0, HI_PROP_B = 1, HI_NA = 2, HI_NB = 3, HI_OFFSET = 4 };
+enum { LI_POS = 0, LI_DIR = 1, LI_WL = 2, LI_WL_START = 3, LI_WL_N = 4 };
+#endif
+
+}  // namespace pvt

@@ -1,0 +1,182 @@
+"""High-level luminescent-solar-concentrator factory (constructor and `add_*` methods of
+pvtrace/device/lsc.py:89-336).
+
+The reference attaches Python subclasses of `FresnelSurfaceDelegate` to the LSC node (`OptionalMirrorAndSolarCell`,
+`AirGapMirror`, lsc.py:22-86), which its compiled engine rejects (compiler.py:239-247).  Here the same options are
+lowered to DATA -- a `FacetSurfaceDelegate` facet table -- so the device traces them:
+
+  back-surface mirror   facet (0,0,-1): reflectivity 1                               (lsc.py:36-37)
+  edge solar cells      facet (+-1,0,0)/(0,+-1,0): reflectivity 0, straight transmit (lsc.py:38-62)
+  air-gap mirror        separate thin n0 box under the LSC, every facet reflectivity 1, specular or Lambertian
+                        (lsc.py:65-86; the reference's "specular" branch returns the *refracted* direction,
+                        a bug we do not reproduce)
+
+`simulate` runs the GPU engine with per-face recorders instead of per-ray pandas rows (lsc.py:338-454).
+"""
+import functools
+
+import numpy as np
+
+from pvtrace_b200.data import lumogen_f_red_305
+from pvtrace_b200.engine.recorder import Histogram, Recorder
+from pvtrace_b200.geometry.box import Box
+from pvtrace_b200.light.light import Light
+from pvtrace_b200.material.component import Absorber, Luminophore, Scatterer
+from pvtrace_b200.material.material import Material
+from pvtrace_b200.material.surface import Facet, FacetSurfaceDelegate, Surface
+from pvtrace_b200.material.utils import cone
+from pvtrace_b200.scene.node import Node
+from pvtrace_b200.scene.scene import Scene
+
+FACES = {"left": (-1, 0, 0), "right": (1, 0, 0), "near": (0, -1, 0), "far": (0, 1, 0), "top": (0, 0, 1),
+         "bottom": (0, 0, -1)}
+
+
+class LSC(object):
+    def __init__(self, size, wavelength_range=None, n0=1.0, n1=1.5):
+        self.wavelength_range = np.arange(400, 800) if wavelength_range is None else wavelength_range
+        self.size = size  # centimetres
+        self.n0, self.n1 = n0, n1
+        self._solar_cell_surfaces = set()
+        self._back_surface_mirror_info = {"want_back_surface_mirror": False}
+        self._air_gap_mirror_info = {"want_air_gap_mirror": False, "lambertian": False}
+        self._scene = None
+        self._result = None
+        self._user_lights = []
+        self._user_components = []
+
+    # -- defaults (lsc.py:115-146) -----------------------------------------------------------
+
+    def _make_default_components(self):
+        x = self.wavelength_range
+        return [
+            {"cls": Luminophore, "name": "Lumogen F Red 305",
+             "coefficient": np.column_stack((x, lumogen_f_red_305.absorption(x) * 10.0)),  # 10 cm-1 at peak
+             "emission": np.column_stack((x, lumogen_f_red_305.emission(x))),
+             "quantum_yield": 1.0, "phase_function": None},
+            {"cls": Absorber, "coefficient": 0.1, "name": "Background"},
+        ]
+
+    def _make_default_lights(self):
+        return [{"name": "Light", "location": (0.0, 0.0, self.size[-1] * 5), "rotation": (np.radians(180), (1, 0, 0)),
+                 "direction": functools.partial(cone, np.radians(20)), "wavelength": None, "position": None}]
+
+    # -- configuration -------------------------------------------------------------------------
+
+    def add_luminophore(self, name, coefficient, emission, quantum_yield, phase_function=None):
+        self._user_components.append({"cls": Luminophore, "name": name, "coefficient": coefficient,
+                                      "emission": emission, "quantum_yield": quantum_yield,
+                                      "phase_function": phase_function})
+
+    def add_absorber(self, name, coefficient):
+        self._user_components.append({"cls": Absorber, "name": name, "coefficient": coefficient})
+
+    def add_scatterer(self, name, coefficient, phase_function=None):
+        self._user_components.append({"cls": Scatterer, "name": name, "coefficient": coefficient,
+                                      "phase_function": phase_function})
+
+    def add_light(self, name, location, rotation=None, direction=None, wavelength=None, position=None):
+        self._user_lights.append({"name": name, "location": location, "rotation": rotation, "direction": direction,
+                                  "wavelength": wavelength, "position": position})
+
+    def add_solar_cell(self, facets):
+        if not isinstance(facets, (list, tuple, set)):
+            raise ValueError("Facets should be a set. e.g. `{'left', 'right'}`")
+        facets = set(facets)
+        allowed = {"left", "near", "far", "right"}
+        if not facets.issubset(allowed):
+            raise ValueError("Solar cell have allowed surfaces", allowed)
+        self._solar_cell_surfaces = facets.union(self._solar_cell_surfaces)
+
+    def add_back_surface_mirror(self):
+        self._back_surface_mirror_info = {"want_back_surface_mirror": True}
+
+    def add_air_gap_mirror(self, lambertian=False):
+        self._air_gap_mirror_info = {"want_air_gap_mirror": True, "lambertian": lambertian}
+
+    def component_names(self):
+        if self._scene is None:
+            raise ValueError("Run a simulation before calling this method.")
+        return {c["name"] for c in self._user_components}
+
+    def light_names(self):
+        if self._scene is None:
+            raise ValueError("Run a simulation before calling this method.")
+        return {light["name"] for light in self._user_lights}
+
+    # -- scene (lsc.py:148-219) --------------------------------------------------------------------
+
+    def _lsc_facets(self):
+        facets = []
+        if self._back_surface_mirror_info["want_back_surface_mirror"]:
+            facets.append(Facet(FACES["bottom"], reflectivity=1.0, atol=1e-8))
+        for name in ("left", "right", "near", "far"):
+            if name in self._solar_cell_surfaces:
+                facets.append(Facet(FACES[name], reflectivity=0.0, transmit="straight", atol=1e-8))
+        return facets
+
+    def _make_scene(self, record=True):
+        (l, w, d) = self.size
+        world = Node(name="World", geometry=Box((l * 100, w * 100, d * 100), material=Material(refractive_index=self.n0)))
+        if len(self._user_components) == 0:
+            self._user_components = self._make_default_components()
+        components = []
+        for spec in self._user_components:
+            spec = dict(spec)
+            cls, coefficient = spec.pop("cls"), spec.pop("coefficient")
+            components.append(cls(coefficient, **spec))
+        lsc = Node(name="LSC", parent=world, geometry=Box((l, w, d), material=Material(
+            refractive_index=self.n1, components=components,
+            surface=Surface(delegate=FacetSurfaceDelegate(self._lsc_facets())))))
+        if self._air_gap_mirror_info["want_air_gap_mirror"]:
+            thickness = 0.25 * d
+            mode = "lambertian" if self._air_gap_mirror_info["lambertian"] else "specular"
+            mirror = Node(name="Air Gap Mirror", parent=world, geometry=Box((l, w, thickness), material=Material(
+                refractive_index=self.n0, components=[],
+                surface=Surface(delegate=FacetSurfaceDelegate(
+                    [Facet(n, reflectivity=1.0, reflect=mode, atol=1e-8) for n in FACES.values()])))))
+            mirror.translate((0.0, 0.0, -(0.5 * d + thickness)))
+        if len(self._user_lights) == 0:
+            self._user_lights = self._make_default_lights()
+        for spec in self._user_lights:
+            node = Node(name=spec["name"], parent=world, light=Light(
+                name=spec["name"], direction=spec["direction"], wavelength=spec["wavelength"],
+                position=spec["position"]))
+            node.location = spec["location"]
+            if spec["rotation"]:
+                node.rotate(*spec["rotation"])
+        if record:
+            wl = (300.0, 1000.0, 100)
+            for face, normal in FACES.items():
+                lsc.recorders.append(Recorder(f"escaping-{face}", event="escaping", facet=normal,
+                                              histograms=[Histogram("wavelength", *wl)]))
+                lsc.recorders.append(Recorder(f"reflected-{face}", event="reflected", facet=normal))
+                lsc.recorders.append(Recorder(f"entering-{face}", event="entering", facet=normal))
+            lsc.recorders.append(Recorder("lost", event="lost", histograms=[Histogram("wavelength", *wl)]))
+            world.recorders.append(Recorder("exit", event="exit"))
+            world.recorders.append(Recorder("killed", event="killed"))
+        self._scene = Scene(world)
+        return self._scene
+
+    # -- run + summary -----------------------------------------------------------------------------
+
+    def simulate(self, n, progress=None, emit_method="kT", seed=None, record_every=0, **engine_kwargs):
+        """Trace `n` rays on the GPU; returns the EngineResult (also kept for `counts()`)."""
+        from pvtrace_b200 import engine
+
+        if self._scene is None:
+            self._make_scene()
+        self._result = engine.simulate(self._scene, n, seed=seed, emit_method=emit_method,
+                                       record_every=record_every, **engine_kwargs)
+        return self._result
+
+    def counts(self):
+        """Distinct-ray counts per LSC face and loss channel: {'escaping': {face: n}, 'reflected': {...},
+        'entering': {...}, 'lost': n, 'exit': n, 'killed': n, 'thrown': n}."""
+        if self._result is None:
+            raise ValueError("Run a simulation before calling this method.")
+        rec = self._result.recorders
+        out = {kind: {face: rec[f"{kind}-{face}"].rays for face in FACES} for kind in ("escaping", "reflected", "entering")}
+        out.update(lost=rec["lost"].rays, exit=rec["exit"].rays, killed=rec["killed"].rays,
+                   thrown=self._result.num_rays)
+        return out
