@@ -161,8 +161,13 @@ typedef struct pvt_params_t {
   int32_t  emit_method;  /* PVT_EMIT_*                                                                    */
   int32_t  rng_mode;     /* PVT_RNG_*                                                                     */
   int32_t  device;       /* CUDA ordinal (host entry points only)                                         */
-  int32_t  flags;        /* reserved, 0                                                                   */
+  int32_t  flags;        /* PVT_FLAG_* bits                                                               */
 } pvt_params_t;
+
+/* Kernel selection.  By default a bundle is traced by the shared-memory wavefront kernel whenever the scene
+ * allows it (Philox stream, <= 64 recorders, tables + photon pool fit in shared memory) and by the
+ * one-photon-per-lane register kernel otherwise; this flag forces the latter (tests cross-check the two). */
+enum { PVT_FLAG_REGISTER_KERNEL = 1 };
 
 /* Run statistics written by every trace (device counters, not estimates). */
 enum {

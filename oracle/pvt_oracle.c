@@ -79,8 +79,15 @@ typedef struct {
   int mode;
   uint64_t s[4]; /* xoshiro state */
   uint64_t id;   /* philox: ray id */
-  uint32_t k;    /* philox: next draw index */
+  uint32_t k;    /* philox: sequential cursor of rng_next() (known-answer helpers only) */
+  uint32_t step; /* philox: trace-loop iteration the addressed draws belong to */
 } rng_t;
+
+/* Draw addressing of the tracer in PHILOX mode (shared definition with pvtrace_b200/csrc/pvt_rng.cuh): every
+ * random decision of a photon step has the fixed address (ray id, step, block, half) -> Philox counter
+ * (id_lo, id_hi, step * 8 + block, stream 0), half selecting the first or second 53-bit uniform of the block.
+ * In XOSHIRO mode addresses are ignored and draws are consumed in program order, which is the reference's. */
+enum { BLOCK_PATH = 0, BLOCK_ABSORB = 1, BLOCK_PHASE = 2, BLOCK_EMIT = 3, BLOCK_LAMBERT = 4, BLOCKS_PER_STEP = 8 };
 
 static uint64_t splitmix64(uint64_t* x) {
   uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
@@ -93,6 +100,7 @@ static void rng_init(rng_t* r, int mode, uint64_t id) {
   r->mode = mode;
   r->id = id;
   r->k = 0;
+  r->step = 0;
   uint64_t x = id;
   for (int i = 0; i < 4; ++i) r->s[i] = splitmix64(&x);
 }
@@ -111,6 +119,11 @@ static double rng_next(rng_t* r) {
     return (double)(result >> 11) * (1.0 / 9007199254740992.0);
   }
   return philox_uniform_at(r->id, 0u, r->k++);
+}
+
+static double rng_draw(rng_t* r, uint32_t block, uint32_t half) {
+  if (r->mode == PVT_RNG_XOSHIRO) return rng_next(r);
+  return philox_uniform_at(r->id, 0u, ((r->step * BLOCKS_PER_STEP + block) << 1) | half);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -278,21 +291,20 @@ static void polar_dir(double theta, double phi, double* out) {
   out[2] = cos(theta);
 }
 
-static void phase_dir(int ptype, double prm, rng_t* rng, double* out) {
+/* g1, g2: the two uniforms of the phase-function draw, in the reference's order of consumption */
+static void phase_dir(int ptype, double prm, double g1, double g2, double* out) {
   double theta, phi;
   if (ptype == PVT_PHASE_HENYEY_GREENSTEIN && fabs(prm) >= EPS_DIST) {
     double g = prm;
-    double s = 2.0 * rng_next(rng) - 1.0;
+    double s = 2.0 * g1 - 1.0;
     double f = (1.0 - g * g) / (1.0 + g * s);
     double mu = 1.0 / (2.0 * g) * (1.0 + g * g - f * f);
-    phi = 2.0 * M_PI * rng_next(rng);
+    phi = 2.0 * M_PI * g2;
     theta = acos(mu);
   } else if (ptype == PVT_PHASE_CONE) {
-    double g1 = rng_next(rng), g2 = rng_next(rng);
     theta = asin(sqrt(g1) * sin(prm));
     phi = 2.0 * M_PI * g2;
   } else {
-    double g1 = rng_next(rng), g2 = rng_next(rng);
     phi = 2.0 * M_PI * g1;
     theta = acos(2.0 * g2 - 1.0);
   }
@@ -439,8 +451,7 @@ static int find_facet(const pvt_scene_t* S, int node, const double* nl) {
 }
 
 /* Lambertian direction about unit vector n (basis chosen so that n = +z reproduces lambertian(), utils.py:173-186) */
-static void lambert_about(const double* n, rng_t* rng, double* out) {
-  double p1 = rng_next(rng), p2 = rng_next(rng);
+static void lambert_about(const double* n, double p1, double p2, double* out) {
   double loc[3];
   polar_dir(asin(sqrt(p1)), 2.0 * M_PI * p2, loc);
   double t1[3], t2[3];
@@ -471,6 +482,7 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
 
   for (;;) {
     ++count;
+    rng.step = (uint32_t)count;
     /* event budget: leave room for the KILL record (:658-663), sampled rays only */
     if (L->base >= 0 && L->n >= L->max_events - 1) {
       log_event(L, PVT_EV_KILL, -1, -1, -1, -1, source, pos, dir, NULL, wl, travelled, duration);
@@ -520,14 +532,14 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
       alpha += interp_clamped(wl, S->abs_x + S->comp_abs_start[c], S->abs_y + S->comp_abs_start[c], S->comp_abs_n[c]);
     }
     double depth = INFINITY;
-    if (alpha > ALPHA_ZERO) depth = -log(1.0 - rng_next(&rng)) / alpha;
+    if (alpha > ALPHA_ZERO) depth = -log(1.0 - rng_draw(&rng, BLOCK_PATH, 0)) / alpha;
 
     if (depth < t0) { /* absorbed in the volume, :762-832 */
       for (int i = 0; i < 3; ++i) pos[i] = pos[i] + dir[i] * depth;
       travelled += depth;
       duration += depth * n_container / C_CM_PER_S;
 
-      double target = rng_next(&rng) * alpha, running = 0.0;
+      double target = rng_draw(&rng, BLOCK_ABSORB, 0) * alpha, running = 0.0;
       int comp = c0;
       for (int k = 0; k < cn; ++k) {
         int c = c0 + k;
@@ -537,9 +549,11 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
       log_event(L, PVT_EV_ABSORB, -1, container, -1, comp, source, pos, dir, NULL, wl, travelled, duration);
 
       const int ctype = S->comp_type[comp];
-      if ((ctype == PVT_COMP_SCATTERER || ctype == PVT_COMP_LUMINOPHORE) && rng_next(&rng) < S->comp_qy[comp]) {
+      if ((ctype == PVT_COMP_SCATTERER || ctype == PVT_COMP_LUMINOPHORE) &&
+          rng_draw(&rng, BLOCK_ABSORB, 1) < S->comp_qy[comp]) {
         double nd[3];
-        phase_dir(S->comp_phase_type[comp], S->comp_phase_param[comp], &rng, nd);
+        double g1 = rng_draw(&rng, BLOCK_PHASE, 0), g2 = rng_draw(&rng, BLOCK_PHASE, 1);
+        phase_dir(S->comp_phase_type[comp], S->comp_phase_param[comp], g1, g2, nd);
         dir[0] = nd[0]; dir[1] = nd[1]; dir[2] = nd[2];
         source = comp;
         if (ctype == PVT_COMP_LUMINOPHORE) { /* component.py:381-440 == :795-812 */
@@ -555,16 +569,16 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
             }
             p1 = interp_clamped(nm, ex, ec, en);
           }
-          double gamma = p1 + (1.0 - p1) * rng_next(&rng);
+          double gamma = p1 + (1.0 - p1) * rng_draw(&rng, BLOCK_EMIT, 0);
           wl = interp_clamped(gamma, ec, ex, en);
-          if (S->comp_tau_rad[comp] > 0.0) duration += -log(1.0 - rng_next(&rng)) * S->comp_tau_rad[comp];
+          if (S->comp_tau_rad[comp] > 0.0) duration += -log(1.0 - rng_draw(&rng, BLOCK_EMIT, 1)) * S->comp_tau_rad[comp];
           log_event(L, PVT_EV_EMIT, -1, container, -1, comp, source, pos, dir, NULL, wl, travelled, duration);
         } else {
           log_event(L, PVT_EV_SCATTER, -1, container, -1, comp, source, pos, dir, NULL, wl, travelled, duration);
         }
         continue;
       }
-      if (S->comp_tau_nr[comp] > 0.0) duration += -log(1.0 - rng_next(&rng)) * S->comp_tau_nr[comp];
+      if (S->comp_tau_nr[comp] > 0.0) duration += -log(1.0 - rng_draw(&rng, BLOCK_EMIT, 1)) * S->comp_tau_nr[comp];
       int sel;
       if (ctype == PVT_COMP_REACTOR) {
         log_event(L, PVT_EV_REACT, -1, container, -1, comp, source, pos, dir, NULL, wl, travelled, duration);
@@ -612,12 +626,13 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
     else if (fresnel) R = fresnel_R(angle, n1, n2);
 
     double u = 1.0;
-    if (R > 0.0) u = rng_next(&rng); /* surface.py:231-240: no draw when R == 0 */
+    if (R > 0.0) u = rng_draw(&rng, BLOCK_PATH, 1); /* surface.py:231-240: no draw when R == 0 */
     double nd[3];
     if (u < R) {
       if (lambert) {
         double back[3] = {-nf[0], -nf[1], -nf[2]}; /* hemisphere the ray arrived from */
-        lambert_about(back, &rng, nd);
+        double p1 = rng_draw(&rng, BLOCK_LAMBERT, 0), p2 = rng_draw(&rng, BLOCK_LAMBERT, 1);
+        lambert_about(back, p1, p2, nd);
       } else {
         mirror_dir(dir, nw, nd);
       }
@@ -830,7 +845,8 @@ int pvt_oracle_sample_phase(int64_t n, int32_t phase_type, double phase_param, u
   for (int64_t i = 0; i < n; ++i) {
     rng_t r;
     rng_init(&r, rng_mode, seed + (uint64_t)i);
-    phase_dir(phase_type, phase_param, &r, out + 3 * i);
+    double g1 = rng_next(&r), g2 = rng_next(&r);
+    phase_dir(phase_type, phase_param, g1, g2, out + 3 * i);
   }
   return 0;
 }

@@ -4,6 +4,7 @@
 // There is no CPU path in this library: every compute entry fails with an error string if CUDA cannot run it.
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -46,6 +47,10 @@ struct pvt_context {
   DeviceBuffer<u64> tallies;
   size_t tally_words = 0;
   DeviceBuffer<double> packed;
+  DeviceBuffer<u64> slabs;  // CTA-private tally slabs of one launch: [max_grid][10 R]
+  int max_grid = 0;
+  int wave_threads = 0;     // CTA size of the wavefront kernel for this scene, 0: scene needs trace_kernel
+  size_t wave_smem = 0;
   // event log of the last trace
   long long log_rows = 0, log_rays = 0;
   DeviceBuffer<int32_t> counts, hit, container, adjacent, component, source;
@@ -103,6 +108,12 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
   return 0;
 }
 
+template <class K>
+static int wave_attr(K kernel, size_t smem) {
+  PVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return 0;
+}
+
 extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context_t** out) {
   if (!out) return fail("ctx out pointer is NULL");
   *out = nullptr;
@@ -124,14 +135,29 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   if (e != cudaSuccess) { delete c; return fail("cudaGetDeviceProperties -> %s", cudaGetErrorString(e)); }
   c->sm_count = prop.multiProcessorCount;
   // the blob lives in shared memory when it leaves room for >= 2 CTAs per SM; otherwise it is read through L1
-  const size_t want = trace_smem_bytes(c->blob_words, c->R());
+  const size_t want = trace_smem_bytes(c->blob_words);
   c->scene_in_smem = want <= (size_t)prop.sharedMemPerBlockOptin && want <= 100 * 1024;
-  c->smem_bytes = trace_smem_bytes(c->scene_in_smem ? c->blob_words : 0, c->R());
+  c->smem_bytes = trace_smem_bytes(c->scene_in_smem ? c->blob_words : 0);
+  // wavefront kernel: needs the blob AND the photon pool in shared memory, <= 64 recorders (seen mask), <= 254 nodes
+  c->wave_threads = 0;
+  if (c->R() <= 64) {
+    int prefer = 1024;
+    if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) prefer = atoi(env);
+    const int choices[3] = {1024, 768, 512};
+    for (int k = 0; k < 3 && prefer > 0; ++k) {
+      const int t = choices[k];
+      if (t > prefer) continue;
+      const size_t need = wavefront_smem_bytes(c->blob_words, t - 64);
+      if (need <= (size_t)prop.sharedMemPerBlockOptin) { c->wave_threads = t; c->wave_smem = need; break; }
+    }
+  }
 
   int rc = c->blob.reserve((size_t)c->blob_words);
   c->tally_words = (size_t)10 * c->R() + c->B() + PVT_NSTATS + 1;
   if (!rc) rc = c->tallies.reserve(c->tally_words);
   if (!rc) rc = c->packed.reserve((size_t)10 * c->R() + c->B() + 1);
+  c->max_grid = c->sm_count * 8;
+  if (!rc) rc = c->slabs.reserve((size_t)c->max_grid * 10 * c->R() + 1);
   if (!rc && cudaMemcpy(c->blob.ptr, c->host_blob.data(), (size_t)c->blob_words * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     rc = fail("scene upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (!rc && cudaMemset(c->tallies.ptr, 0, c->tally_words * 8) != cudaSuccess)
@@ -140,6 +166,9 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   if (!rc) rc = occupancy(trace_kernel<PhiloxStream, 8>, c->smem_bytes, &c->blocks_per_sm[1]);
   if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 2>, c->smem_bytes, &c->blocks_per_sm[2]);
   if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 8>, c->smem_bytes, &c->blocks_per_sm[3]);
+  if (!rc && c->wave_threads == 1024) rc = wave_attr(wavefront_kernel<1024>, c->wave_smem);
+  if (!rc && c->wave_threads == 768) rc = wave_attr(wavefront_kernel<768>, c->wave_smem);
+  if (!rc && c->wave_threads == 512) rc = wave_attr(wavefront_kernel<512>, c->wave_smem);
   if (!rc && c->smem_bytes > 48 * 1024 &&
       cudaFuncSetAttribute(intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess)
     rc = fail("cudaFuncSetAttribute(intersect_kernel) failed");
@@ -154,7 +183,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
 extern "C" int pvt_context_destroy(pvt_context_t* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  c->blob.release(); c->tallies.release(); c->packed.release();
+  c->blob.release(); c->tallies.release(); c->packed.release(); c->slabs.release();
   c->counts.release(); c->hit.release(); c->container.release(); c->adjacent.release(); c->component.release();
   c->source.release(); c->kind.release(); c->position.release(); c->direction.release(); c->normal.release();
   c->wavelength.release(); c->travelled.release(); c->duration.release();
@@ -242,16 +271,35 @@ extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const dou
                      c->source.ptr, c->position.ptr, c->direction.ptr, c->normal.ptr, c->wavelength.ptr,
                      c->travelled.ptr, c->duration.ptr};
 
-  const int wide = c->R() > 64;
-  const int which = (P->rng_mode == PVT_RNG_XOSHIRO ? 2 : 0) + wide;
-  long long want_blocks = (P->n + kTraceThreads - 1) / kTraceThreads;
-  const long long resident = (long long)c->sm_count * c->blocks_per_sm[which];
-  const int grid = (int)(want_blocks < resident ? want_blocks : resident);
-  switch (which) {
-    case 0: trace_kernel<PhiloxStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-    case 1: trace_kernel<PhiloxStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-    case 2: trace_kernel<XoshiroStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-    default: trace_kernel<XoshiroStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+  a.slabs = c->slabs.ptr;
+  const bool megakernel_forced = (P->flags & PVT_FLAG_REGISTER_KERNEL) != 0;
+  int grid;
+  if (c->wave_threads > 0 && P->rng_mode == PVT_RNG_PHILOX && !megakernel_forced) {
+    // one persistent CTA per SM, each owning a contiguous slice of the photon range
+    const int pool = c->wave_threads - 64;
+    const long long want_blocks = (P->n + pool - 1) / pool;
+    grid = (int)(want_blocks < c->sm_count ? want_blocks : c->sm_count);
+    if (P->n / grid >= (1ll << 31)) return fail("bundle too large: at most 2^31 rays per SM per call");
+    PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
+    switch (c->wave_threads) {
+      case 1024: wavefront_kernel<1024><<<grid, 1024, c->wave_smem, st>>>(a); break;
+      case 768: wavefront_kernel<768><<<grid, 768, c->wave_smem, st>>>(a); break;
+      default: wavefront_kernel<512><<<grid, 512, c->wave_smem, st>>>(a); break;
+    }
+  } else {
+    const int wide = c->R() > 64;
+    const int which = (P->rng_mode == PVT_RNG_XOSHIRO ? 2 : 0) + wide;
+    long long want_blocks = (P->n + kTraceThreads - 1) / kTraceThreads;
+    long long resident = (long long)c->sm_count * c->blocks_per_sm[which];
+    if (resident > c->max_grid) resident = c->max_grid;
+    grid = (int)(want_blocks < resident ? want_blocks : resident);
+    PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
+    switch (which) {
+      case 0: trace_kernel<PhiloxStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+      case 1: trace_kernel<PhiloxStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+      case 2: trace_kernel<XoshiroStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+      default: trace_kernel<XoshiroStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
+    }
   }
   PVT_CUDA(cudaGetLastError());
   c->launches += 1;

@@ -1,12 +1,23 @@
 // pvt_kernels.cuh -- the CUDA kernels of libpvtrace_b200.so (sm_100a).
 //
-//   trace_kernel      persistent-threads photon tracer.  One CTA per SM slot for the whole launch; the scene blob
-//                     is staged into shared memory once per CTA by a single TMA bulk copy (cp.async.bulk +
-//                     mbarrier); every lane owns one live photon in registers and advances it one step per loop
-//                     iteration; lanes whose photon retired are found by warp ballot and refilled from a
-//                     warp-private reservoir of photon indices, itself refilled from one global counter.  All
-//                     randomness is counter based (photon index, draw number), so the schedule is invisible in
-//                     the results.
+//   wavefront_kernel  THE tracer.  Persistent CTAs (one per SM) that each own a contiguous slice of the photon
+//                     index range and a pool of live photons held as a structure of arrays in SHARED MEMORY.
+//                     Every loop iteration runs two barrier-separated stages over the pool:
+//                       1. refill + classify: each pool slot is served by its home thread; retired slots take the
+//                          next photon of the slice (coalesced load of the initial-ray arrays, or on-device
+//                          emission); live photons are intersected with every node and draw their free path;
+//                          the slot index is appended to the VOLUME, SURFACE or EXIT queue (warp ballot +
+//                          one shared-memory atomic per warp);
+//                       2. interact: the three queues are laid end to end, padded to warp boundaries, and
+//                          thread e serves entry e -- so every warp executes ONE kind of interaction with all
+//                          lanes busy, instead of every warp executing all kinds with a few lanes each.
+//                     The scene blob is staged into shared memory once per CTA by a single TMA bulk copy
+//                     (cp.async.bulk + mbarrier).  Random numbers are addressed by (photon, step, purpose), so
+//                     neither the regrouping nor the CTA count is visible in the results.
+//   trace_kernel      the same physics with one photon per lane held in registers (persistent threads, warp
+//                     ballot refill from a global counter).  Handles everything the pool kernel does not:
+//                     the reference's sequential xoshiro stream, more than 64 recorders, scenes too large for
+//                     shared memory.  Also the cross-check of the wavefront kernel in the tests.
 //   intersect_kernel  the ray/primitive stage on its own over a photon array (next_hit + find_container).
 //   emit_kernel       initial rays of the built-in light delegates.
 //   *_test kernels    one thin launch per device helper for the known-answer tests.
@@ -32,6 +43,7 @@ struct TraceArgs {
   u64 seed;
   StepParams sp;
   u64* work_counter;
+  u64* slabs;       // [gridDim.x][10 R] CTA-private tally slabs, zero on entry
   u64* g_distinct;  // [R]
   u64* g_cross;     // [R]
   double* g_sums;   // [R,8]
@@ -71,34 +83,253 @@ __device__ __forceinline__ void stage_blob(double* dst, const double* src, uint3
   }
 }
 
-// shared memory layout of trace_kernel: [mbarrier 16 B][blob][slab: distinct R | cross R | sums 8R]
-__host__ __device__ inline size_t trace_smem_bytes(int blob_words_in_smem, int n_recorders) {
-  return 16 + (size_t)blob_words_in_smem * 8 + (size_t)n_recorders * 10 * 8;
+__device__ __forceinline__ TallySink cta_sink(const TraceArgs& a, int R) {
+  u64* slab = a.slabs + (size_t)blockIdx.x * 10 * R;
+  return TallySink{slab, slab + R, reinterpret_cast<double*>(slab + 2 * R), a.g_bins};
 }
+
+// adds the CTA's slab into the context accumulators and the lanes' statistics into g_stats
+__device__ __forceinline__ void retire_cta(const TraceArgs& a, int R, const LaneStats& st) {
+  u64 s_steps = st.steps, s_events = st.events, s_rays = st.rays;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    s_steps += __shfl_down_sync(kFullMask, s_steps, off);
+    s_events += __shfl_down_sync(kFullMask, s_events, off);
+    s_rays += __shfl_down_sync(kFullMask, s_rays, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(a.g_stats + PVT_STAT_STEPS, s_steps);
+    atomicAdd(a.g_stats + PVT_STAT_EVENTS, s_events);
+    atomicAdd(a.g_stats + PVT_STAT_RAYS, s_rays);
+  }
+  __threadfence();  // this thread's reductions into the slab are performed before the barrier below
+  __syncthreads();
+  const u64* slab = a.slabs + (size_t)blockIdx.x * 10 * R;
+  for (int k = threadIdx.x; k < R * 10; k += blockDim.x) {
+    const u64 v = __ldcg(slab + k);
+    if (k < R) { if (v) atomicAdd(a.g_distinct + k, v); }
+    else if (k < 2 * R) { if (v) atomicAdd(a.g_cross + (k - R), v); }
+    else {
+      const double x = __longlong_as_double((long long)v);
+      if (x != 0.0) atomicAdd(a.g_sums + (k - 2 * R), x);
+    }
+  }
+}
+
+// =========================================================================================================
+// wavefront_kernel
+
+// Shared-memory pool of P photon slots, structure of arrays.  kPoolDoubles double columns, then 64-bit, 32-bit
+// and 16-bit columns; column c of slot s is at base + c * P + s.
+constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
+constexpr int kPoolWords = 5;     // count (< 0: slot is empty), source, nlog (< 0: ray not sampled), idx, ids
+__host__ __device__ constexpr size_t pool_bytes(int P) {
+  return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + 64 /*counters*/;
+}
+__host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
+  return 16 + (size_t)blob_words * 8 + pool_bytes(P);
+}
+
+struct PoolView {
+  double *px, *py, *pz, *dx, *dy, *dz, *wl, *trav, *dur, *t, *u, *alpha;
+  u64* seen;
+  int32_t *count, *source, *nlog;
+  uint32_t *idx, *ids;
+  uint16_t *qv, *qs, *qe;
+  uint32_t* counters;  // [2][4] queue lengths, double buffered by iteration parity; [8..9] next index of the slice
+};
+
+__device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
+  PoolView v;
+  double* d = reinterpret_cast<double*>(base);
+  v.px = d; v.py = d + P; v.pz = d + 2 * P; v.dx = d + 3 * P; v.dy = d + 4 * P; v.dz = d + 5 * P;
+  v.wl = d + 6 * P; v.trav = d + 7 * P; v.dur = d + 8 * P; v.t = d + 9 * P; v.u = d + 10 * P; v.alpha = d + 11 * P;
+  v.seen = reinterpret_cast<u64*>(d + 12 * P);
+  int32_t* w = reinterpret_cast<int32_t*>(d + 13 * P);
+  v.count = w; v.source = w + P; v.nlog = w + 2 * P;
+  v.idx = reinterpret_cast<uint32_t*>(w + 3 * P); v.ids = reinterpret_cast<uint32_t*>(w + 4 * P);
+  uint16_t* h = reinterpret_cast<uint16_t*>(w + 5 * P);
+  v.qv = h; v.qs = h + P; v.qe = h + 2 * P;
+  v.counters = reinterpret_cast<uint32_t*>(h + 3 * P);  // P is a multiple of 32: 4-byte aligned
+  return v;
+}
+
+typedef PhotonT<2> PoolPhoton;
+
+__device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, long long slice_lo,
+                                          long long record_every, int max_events) {
+  ph.p = V3{pool.px[s], pool.py[s], pool.pz[s]};
+  ph.d = V3{pool.dx[s], pool.dy[s], pool.dz[s]};
+  ph.wl = pool.wl[s]; ph.travelled = pool.trav[s]; ph.duration = pool.dur[s];
+  ph.count = pool.count[s]; ph.source = pool.source[s]; ph.nlog = pool.nlog[s];
+  const u64 seen = pool.seen[s];
+  ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
+  ph.log_base = -1;
+  if (ph.nlog >= 0) ph.log_base = ((long long)pool.idx[s] + slice_lo) / record_every * (long long)max_events;
+}
+__device__ __forceinline__ void store_slot(const PoolView& pool, int s, const PoolPhoton& ph) {
+  pool.px[s] = ph.p.x; pool.py[s] = ph.p.y; pool.pz[s] = ph.p.z;
+  pool.dx[s] = ph.d.x; pool.dy[s] = ph.d.y; pool.dz[s] = ph.d.z;
+  pool.wl[s] = ph.wl; pool.trav[s] = ph.travelled; pool.dur[s] = ph.duration;
+  pool.source[s] = ph.source; pool.nlog[s] = ph.nlog;
+  pool.seen[s] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);
+}
+
+// append slot `s` to queue `q` for the lanes where `pred` holds: one shared atomic per warp
+__device__ __forceinline__ void push_queue(uint16_t* q, uint32_t* counter, bool pred, int s, int lane) {
+  const unsigned m = __ballot_sync(kFullMask, pred);
+  if (m == 0) return;
+  uint32_t base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(kFullMask, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)s;
+}
+
+template <int T>
+__global__ void __launch_bounds__(T, 1) wavefront_kernel(const TraceArgs a) {
+  constexpr int P = T - 64;  // two warps have no home slot: room for the warp padding of the queues in stage 2
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* sblob = reinterpret_cast<double*>(smem_raw + 16);
+  stage_blob(sblob, a.blob, (uint32_t)a.blob_words * 8u, bar);
+  const SceneView sv{sblob};
+  const PoolView pool = carve_pool(smem_raw + 16 + (size_t)a.blob_words * 8, P);
+  const int R = sv.hdr().n_recorders;
+  const TallySink sink = cta_sink(a, R);
+  const PhiloxStream rng0{a.seed + (u64)a.first_index, 0u, 0u};
+  const StepParams sp = a.sp;
+  const LogColumns& L = a.log;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  // contiguous slice of the photon range owned by this CTA
+  const long long slice_lo = a.n * (long long)blockIdx.x / gridDim.x;
+  const long long slice_hi = a.n * (long long)(blockIdx.x + 1) / gridDim.x;
+  const uint32_t slice_n = (uint32_t)(slice_hi - slice_lo);
+  if (tid < 12) pool.counters[tid] = 0u;
+  if (tid < P) pool.count[tid] = -1;
+  __syncthreads();
+
+  LaneStats st;
+  for (uint32_t iter = 0;; ++iter) {
+    uint32_t* qn = pool.counters + 4 * (iter & 1);
+    // ---------------- stage 1: refill + classify, slot == tid -----------------------------------------
+    bool live = false;
+    if (tid < P) {
+      PoolPhoton ph;
+      const bool dead = pool.count[tid] < 0;
+      const unsigned m = __ballot_sync(kFullMask, dead);
+      bool fresh = false;
+      if (m) {
+        uint32_t base = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) base = atomicAdd(pool.counters + 8, (uint32_t)__popc(m));
+        base = __shfl_sync(kFullMask, base, leader);
+        const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
+        if (dead && mine < slice_n) {
+          const long long i = slice_lo + mine;
+          const u64 id = rng0.id + (u64)i;
+          if (a.pos) {
+            ph.p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
+            ph.d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
+            ph.wl = a.wl[i];
+          } else {
+            emit_ray(sv, id, a.first_index + i, ph.p, ph.d, ph.wl);
+          }
+          ph.log_base = -1;
+          if (a.record_every > 0 && i % a.record_every == 0) ph.log_base = i / a.record_every * (long long)sp.max_events;
+          begin_photon(ph, L, sp, st);
+          if (ph.log_base < 0) ph.nlog = -1;
+          pool.idx[tid] = mine;
+          fresh = true;
+        }
+      }
+      StepClass cls = kDead;
+      if (fresh || !dead) {
+        if (!fresh) load_slot(pool, tid, ph, slice_lo, a.record_every, sp.max_events);
+        PhiloxStream rng = rng0;
+        rng.id += (u64)(slice_lo + pool.idx[tid]);
+        StepPlan plan;
+        cls = classify_step(sv, sink, L, sp, ph, rng, st, plan);
+        if (cls == kDead) {
+          if (ph.log_base >= 0) L.counts[ph.log_base / sp.max_events] = ph.nlog;
+          pool.count[tid] = -1;
+        } else {
+          if (fresh) store_slot(pool, tid, ph);
+          pool.count[tid] = ph.count;
+          pool.t[tid] = plan.t; pool.u[tid] = plan.u; pool.alpha[tid] = plan.alpha;
+          pool.ids[tid] = (uint32_t)(plan.hit & 0xff) | ((uint32_t)(plan.container & 0xff) << 8) |
+                          ((uint32_t)(plan.adjacent & 0xff) << 16);
+          live = true;
+        }
+      }
+      push_queue(pool.qv, qn + 0, cls == kVolume, tid, lane);
+      push_queue(pool.qs, qn + 1, cls == kSurface, tid, lane);
+      push_queue(pool.qe, qn + 2, cls == kExit, tid, lane);
+    }
+    if (!__syncthreads_or(live)) break;
+
+    // ---------------- stage 2: interact, thread e serves queue entry e ------------------------------------
+    const int cv = (int)qn[0], cs = (int)qn[1], ce = (int)qn[2];
+    const int pv = (cv + 31) & ~31, ps = (cs + 31) & ~31;
+    if (tid < 4) pool.counters[4 * ((iter + 1) & 1) + tid] = 0u;
+    int slot = -1, cls = kDead;
+    if (tid < pv) { if (tid < cv) { slot = pool.qv[tid]; cls = kVolume; } }
+    else if (tid < pv + ps) { if (tid - pv < cs) { slot = pool.qs[tid - pv]; cls = kSurface; } }
+    else if (tid - pv - ps < ce) { slot = pool.qe[tid - pv - ps]; cls = kExit; }
+    if (slot >= 0) {
+      PoolPhoton ph;
+      load_slot(pool, slot, ph, slice_lo, a.record_every, sp.max_events);
+      PhiloxStream rng = rng0;
+      rng.id += (u64)(slice_lo + pool.idx[slot]);
+      rng.begin_step((uint32_t)ph.count);
+      StepPlan plan;
+      plan.t = pool.t[slot]; plan.u = pool.u[slot]; plan.alpha = pool.alpha[slot];
+      const uint32_t ids = pool.ids[slot];
+      plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
+      if (plan.adjacent == 0xff) plan.adjacent = -1;
+      bool alive;
+      if (cls == kVolume) alive = volume_step(sv, sink, L, sp, ph, rng, st, plan);
+      else if (cls == kSurface) alive = surface_step(sv, sink, L, sp, ph, rng, st, plan);
+      else { exit_step(sv, sink, L, sp, ph, st, plan); alive = false; }
+      if (alive) {
+        store_slot(pool, slot, ph);
+      } else {
+        if (ph.log_base >= 0) L.counts[ph.log_base / sp.max_events] = ph.nlog;
+        pool.count[slot] = -1;
+      }
+    }
+    __syncthreads();
+  }
+  retire_cta(a, R, st);
+}
+
+// =========================================================================================================
+// trace_kernel: one photon per lane in registers
+
+// shared memory layout of trace_kernel: [mbarrier 16 B][blob]
+__host__ __device__ inline size_t trace_smem_bytes(int blob_words_in_smem) { return 16 + (size_t)blob_words_in_smem * 8; }
 
 template <class Rng, int SW>
 __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
-  const int words_in_smem = a.scene_in_smem ? a.blob_words : 0;
-  u64* slab = reinterpret_cast<u64*>(smem_raw + 16 + (size_t)words_in_smem * 8);
-
   if (a.scene_in_smem) stage_blob(sblob, a.blob, (uint32_t)a.blob_words * 8u, bar);
   const SceneView sv{a.scene_in_smem ? sblob : a.blob};
   const int R = sv.hdr().n_recorders;
-  for (int k = threadIdx.x; k < R * 10; k += blockDim.x) slab[k] = 0ull;
-  __syncthreads();
-  const TallySink T{slab, slab + R, reinterpret_cast<double*>(slab + 2 * R), a.g_bins};
+  const TallySink sink = cta_sink(a, R);
+  const StepParams sp = a.sp;
+  const LogColumns& L = a.log;
 
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  Photon<Rng, SW> ph;
-  ph.nsteps = 0; ph.nevents = 0;
+  PhotonT<SW> ph;
+  Rng rng;
   ph.log_base = -1; ph.nlog = 0;
   bool alive = false, exhausted = false;
   long long res_next = 0, res_end = 0;  // warp-uniform reservoir [res_next, res_end) of photon indices
-  uint32_t rays = 0;
+  LaneStats st;
 
   for (;;) {
     const unsigned need = __ballot_sync(kFullMask, !alive && !exhausted);
@@ -132,12 +363,11 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
           } else {
             emit_ray(sv, id, a.first_index + idx, ph.p, ph.d, ph.wl);
           }
-          ph.rng.init(id);
+          rng.init(id);
           ph.log_base = -1;
-          if (a.record_every > 0 && idx % a.record_every == 0) ph.log_base = (idx / a.record_every) * (long long)a.sp.max_events;
-          begin_photon(ph, a.log, a.sp);
+          if (a.record_every > 0 && idx % a.record_every == 0) ph.log_base = (idx / a.record_every) * (long long)sp.max_events;
+          begin_photon(ph, L, sp, st);
           alive = true;
-          ++rays;
         } else {
           exhausted = true;  // the global counter is past n: nothing will ever arrive
         }
@@ -145,37 +375,21 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
     }
     if (!__any_sync(kFullMask, alive)) break;
     if (alive) {
-      alive = step_photon(sv, T, a.log, a.sp, ph);
+      StepPlan plan;
+      const StepClass cls = classify_step(sv, sink, L, sp, ph, rng, st, plan);
+      if (cls == kVolume) alive = volume_step(sv, sink, L, sp, ph, rng, st, plan);
+      else if (cls == kSurface) alive = surface_step(sv, sink, L, sp, ph, rng, st, plan);
+      else {
+        if (cls == kExit) exit_step(sv, sink, L, sp, ph, st, plan);
+        alive = false;
+      }
       if (!alive && ph.log_base >= 0) {  // a sampled ray publishes its event count when it retires
-        a.log.counts[ph.log_base / a.sp.max_events] = ph.nlog;
+        L.counts[ph.log_base / sp.max_events] = ph.nlog;
         ph.log_base = -1;
       }
     }
   }
-
-  // run statistics: one atomic per warp per counter
-  u64 s_steps = ph.nsteps, s_events = ph.nevents, s_rays = rays;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    s_steps += __shfl_down_sync(kFullMask, s_steps, off);
-    s_events += __shfl_down_sync(kFullMask, s_events, off);
-    s_rays += __shfl_down_sync(kFullMask, s_rays, off);
-  }
-  if (lane == 0) {
-    atomicAdd(a.g_stats + PVT_STAT_STEPS, s_steps);
-    atomicAdd(a.g_stats + PVT_STAT_EVENTS, s_events);
-    atomicAdd(a.g_stats + PVT_STAT_RAYS, s_rays);
-  }
-  // flush the CTA's tally slab
-  __syncthreads();
-  for (int k = threadIdx.x; k < R * 10; k += blockDim.x) {
-    if (k < R) { if (slab[k]) atomicAdd(a.g_distinct + k, slab[k]); }
-    else if (k < 2 * R) { if (slab[k]) atomicAdd(a.g_cross + (k - R), slab[k]); }
-    else {
-      const double v = reinterpret_cast<double*>(slab)[k];
-      if (v != 0.0) atomicAdd(a.g_sums + (k - 2 * R), v);
-    }
-  }
+  retire_cta(a, R, st);
 }
 
 // ---- the intersect stage on its own ----------------------------------------------------------------------
@@ -295,7 +509,8 @@ __global__ void test_phase_kernel(long long n, int ptype, double prm, u64 seed, 
   if (i >= n) return;
   Rng rng;
   rng.init(seed + (u64)i);
-  const V3 r = phase_direction(ptype, prm, rng);
+  const double g1 = rng.next(), g2 = rng.next();  // uniforms 0 and 1 of the ray's stream
+  const V3 r = phase_direction(ptype, prm, g1, g2);
   out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
 }
 

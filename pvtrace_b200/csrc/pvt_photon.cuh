@@ -1,12 +1,15 @@
-// pvt_photon.cuh -- one photon on one lane: state, nearest-surface search, tallies, event log, and the
-// step function (one iteration of the trace loop = one "photon step", the unit of work of SURVEY 8d).
+// pvt_photon.cuh -- the physics of one photon step, split into the stages the kernels schedule:
+//
+//   classify_step   next_hit + find_container + Beer-Lambert free path  -> EXIT | VOLUME | SURFACE | dead
+//   volume_step     absorption: component pick, re-emission (phase function, spectral CDF) or loss
+//   surface_step    normal, Fresnel (or facet) reflectivity, reflect / refract
+//   exit_step       leaves through the root boundary
 //
 // Behaviour follows the reference's compiled tracer, pvtrace/engine/_kernel.pyx:603-897 (which replicates
-// pvtrace/algorithm/photon_tracer.py:112-273); the citations on each block point at the lines reproduced.
-// The code is written for the GPU, not transcribed: hits are reduced on the fly instead of being stored and
-// sorted, scene records are read as shared-memory broadcasts, tallies go to a CTA-private shared slab and
-// to global histogram bins with fire-and-forget atomics, and all random numbers come from a counter-based
-// stream addressed by the photon's global index.
+// pvtrace/algorithm/photon_tracer.py:112-273); citations on each block point at the lines reproduced.  The
+// code is written for the GPU, not transcribed: hits are reduced on the fly instead of stored and sorted,
+// scene records are shared-memory broadcasts, angles are carried as cosines (acos only when a recorder asks),
+// tallies are fire-and-forget reductions, and every random number has a fixed counter address (pvt_rng.cuh).
 #pragma once
 #include "pvt_math.cuh"
 #include "pvt_rng.cuh"
@@ -24,25 +27,32 @@ struct LogColumns {
   double *position, *direction, *normal, *wavelength, *travelled, *duration;
 };
 
-// Where tallies go: a shared-memory slab private to the CTA for the per-recorder scalars (every lane of the
-// chip hammers the same few addresses otherwise) and global memory for histogram bins (spread addresses).
+// Where tallies go.  Per-recorder scalars (distinct, crossings, 8 moment sums) go to a slab PRIVATE TO THE CTA in
+// global memory, written with reductions that do not return (RED): no CAS loops, no contention between CTAs;
+// the kernel folds the slab into the context's accumulators when the CTA retires.  Histogram bins are spread
+// addresses and go straight to the shared accumulator.
 struct TallySink {
-  u64* distinct;  // [R] shared
-  u64* cross;     // [R] shared
-  double* sums;   // [R,8] shared
-  u64* bins;      // [total_bins] global
+  u64* distinct;  // [R]   CTA slab
+  u64* cross;     // [R]
+  double* sums;   // [R,8]
+  u64* bins;      // [total_bins] context accumulator
 };
 
-template <class Rng, int kSeenWords>
-struct Photon {
+struct StepParams {
+  int maxsteps, max_events, emit_method;
+};
+
+// Photon state carried between steps.  `seen` is the distinct-ray mask of up to 32 * kSeenWords recorders.
+template <int kSeenWords>
+struct PhotonT {
   V3 p, d;
   double wl, travelled, duration;
-  Rng rng;
   int32_t source, count, nlog;
   long long log_base;  // first log row of this ray, < 0 when the ray is not sampled
   uint32_t seen[kSeenWords];
-  uint32_t nsteps, nevents;  // run statistics carried by the lane
 };
+
+enum StepClass { kDead = 0, kExit = 1, kVolume = 2, kSurface = 3 };
 
 struct Nearest {
   double t0;
@@ -98,13 +108,12 @@ __device__ __forceinline__ double absorption_at(const SceneView& sv, int c, doub
   return interp_hinted(x, sv.w + h.off_abs_x + start, sv.w + h.off_abs_y + start, n, sv.comp(c)[kCompAbsInvDx]);
 }
 
-// ---- event log (_kernel.pyx:562-597) ---------------------------------------------------------------------
+// ---- event log (_kernel.pyx:562-597).  Out of line: only sampled rays ever get here. ----------------------
 
 template <class P>
-__device__ __forceinline__ void log_event(const LogColumns& L, int max_events, P& ph, int kind, int hit, int container,
-                                          int adjacent, int component, const V3* normal) {
-  ++ph.nevents;
-  if (ph.log_base < 0 || ph.nlog >= max_events) return;
+__device__ __noinline__ void log_event(const LogColumns& L, int max_events, P& ph, int kind, int hit, int container,
+                                       int adjacent, int component, const V3* normal) {
+  if (ph.nlog >= max_events) return;
   const long long row = ph.log_base + ph.nlog;
   L.kind[row] = (uint8_t)kind;
   L.hit[row] = hit; L.container[row] = container; L.adjacent[row] = adjacent;
@@ -115,6 +124,7 @@ __device__ __forceinline__ void log_event(const LogColumns& L, int max_events, P
   L.wavelength[row] = ph.wl; L.travelled[row] = ph.travelled; L.duration[row] = ph.duration;
   ++ph.nlog;
 }
+#define PVT_LOG(ph, ...) do { if ((ph).log_base >= 0) log_event(L, sp.max_events, ph, __VA_ARGS__); } while (0)
 
 // ---- tallies (_kernel.pyx:501-556; semantics restated by engine/tally.py:26-47,86-156) -------------------
 
@@ -131,22 +141,26 @@ __device__ __forceinline__ double ray_property(int prop, double wl, double angle
   }
 }
 
+// `cosine` is the cosine of the incidence angle (1 for volume events => angle 0); acos is taken only if a
+// recorder actually matches for the first time.
 template <class P>
-__device__ __noinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, int sel, int node,
-                                   const V3* wnormal, const V3& lp, double angle) {
+__device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, int sel, int node,
+                                      bool has_normal, const V3& wnormal, const V3& lp, double cosine) {
   const int R = sv.hdr().n_recorders;
+  double angle = -1.0;
   for (int r = 0; r < R; ++r) {
     if (sv.rec_int(r, RI_NODE) != node || sv.rec_int(r, RI_EVENT) != sel) continue;
     const double* q = sv.rec(r);
     if (sv.rec_int(r, RI_HAS_FACET)) {
-      if (!wnormal) continue;
+      if (!has_normal) continue;
       const double tol = q[kRecAtol];
-      if (fabs(q[0] - wnormal->x) > tol || fabs(q[1] - wnormal->y) > tol || fabs(q[2] - wnormal->z) > tol) continue;
+      if (fabs(q[0] - wnormal.x) > tol || fabs(q[1] - wnormal.y) > tol || fabs(q[2] - wnormal.z) > tol) continue;
     }
     atomicAdd(&T.cross[r], 1ull);
     const uint32_t bit = 1u << (r & 31);
     if (ph.seen[r >> 5] & bit) continue;
     ph.seen[r >> 5] |= bit;
+    if (angle < 0.0) angle = cosine >= 1.0 ? 0.0 : acos(cosine);
     atomicAdd(&T.distinct[r], 1ull);
     double* m = T.sums + 8 * r;
     atomicAdd(m + 0, ph.wl);         atomicAdd(m + 1, ph.wl * ph.wl);
@@ -184,10 +198,6 @@ __device__ __forceinline__ int find_facet(const SceneView& sv, int node, const V
   return -1;
 }
 
-struct StepParams {
-  int maxsteps, max_events, emit_method;
-};
-
 template <class P>
 __device__ __forceinline__ void advance(P& ph, double t, double n_container) {
   ph.p = axpy(ph.p, ph.d, t);
@@ -195,121 +205,187 @@ __device__ __forceinline__ void advance(P& ph, double t, double n_container) {
   ph.duration += t * n_container / kLightSpeed;
 }
 
-template <class Rng, int SW>
-__device__ __forceinline__ void begin_photon(Photon<Rng, SW>& ph, const LogColumns& L, const StepParams& sp) {
+// Per-lane run statistics (device counters of pvt_out_t.stats)
+struct LaneStats {
+  uint32_t steps = 0, events = 0, rays = 0;
+};
+
+template <class P>
+__device__ __forceinline__ void begin_photon(P& ph, const LogColumns& L, const StepParams& sp, LaneStats& st) {
   ph.travelled = 0.0; ph.duration = 0.0;
   ph.source = -1; ph.count = 0; ph.nlog = 0;
 #pragma unroll
-  for (int w = 0; w < SW; ++w) ph.seen[w] = 0u;
-  log_event(L, sp.max_events, ph, PVT_EV_GENERATE, -1, -1, -1, -1, nullptr);
+  for (int w = 0; w < (int)(sizeof(ph.seen) / 4); ++w) ph.seen[w] = 0u;
+  ++st.rays; ++st.events;
+  PVT_LOG(ph, PVT_EV_GENERATE, -1, -1, -1, -1, nullptr);
 }
 
-// One iteration of the reference's `while True` (_kernel.pyx:654-895).  Returns true while the photon lives.
-template <class Rng, int SW>
-__device__ __forceinline__ bool step_photon(const SceneView& sv, const TallySink& T, const LogColumns& L,
-                                            const StepParams& sp, Photon<Rng, SW>& ph) {
-  typedef Photon<Rng, SW> P;
+// What classify_step hands to the second stage
+struct StepPlan {
+  double t;    // distance to the event: free path (VOLUME) or surface distance (SURFACE, EXIT)
+  double u;    // the surface uniform of this step (address kBlockPath half 1); philox streams fetch it here
+  double alpha;
+  int hit, container, adjacent;
+};
+
+// First half of the reference's loop body (_kernel.pyx:654-760): budget check, intersect, kill check, free path.
+template <class Rng, class P>
+__device__ __forceinline__ StepClass classify_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
+                                                   const StepParams& sp, P& ph, Rng& rng, LaneStats& st, StepPlan& plan) {
   const Header& H = sv.hdr();
-  const bool have_rec = H.n_recorders > 0;
+  plan.u = 1.0; plan.alpha = 0.0;
   ++ph.count;
+  rng.begin_step((uint32_t)ph.count);
   // event budget of sampled rays: keep room for the KILL record (:658-663)
   if (ph.log_base >= 0 && ph.nlog >= sp.max_events - 1) {
-    log_event(L, sp.max_events, ph, PVT_EV_KILL, -1, -1, -1, -1, nullptr);
-    return false;
+    ++st.events;
+    PVT_LOG(ph, PVT_EV_KILL, -1, -1, -1, -1, nullptr);
+    return kDead;
   }
-  ++ph.nsteps;
+  ++st.steps;
   const Nearest nh = nearest_surface(sv, ph.p, ph.d);
-  if (nh.total == 0) return false;  // :681-682
-  const int hit = nh.hit, container = nh.container, adjacent = nh.adjacent;
-  const double t0 = nh.t0;
+  if (nh.total == 0) return kDead;  // :681-682
+  plan.hit = nh.hit; plan.container = nh.container; plan.adjacent = nh.adjacent;
+  plan.t = nh.t0;
 
   if (ph.count > sp.maxsteps) {  // :716-723
-    log_event(L, sp.max_events, ph, PVT_EV_KILL, -1, container, -1, -1, nullptr);
-    if (have_rec) {
-      const V3 lp = map_point(sv.node(container) + kNodeW2L, ph.p);
-      tally<P>(sv, T, ph, PVT_REC_KILLED, container, nullptr, lp, 0.0);
+    ++st.events;
+    PVT_LOG(ph, PVT_EV_KILL, -1, nh.container, -1, -1, nullptr);
+    if (H.n_recorders > 0) {
+      const V3 lp = map_point(sv.node(nh.container) + kNodeW2L, ph.p);
+      tally(sv, T, ph, PVT_REC_KILLED, nh.container, false, V3{0.0, 0.0, 0.0}, lp, 1.0);
     }
-    return false;
+    return kDead;
   }
-
-  const double n_container = sv.node(container)[kNodeIndex];
-
-  if (hit == H.root_id) {  // leaves the scene, :728-744
-    advance(ph, t0, n_container);
-    log_event(L, sp.max_events, ph, PVT_EV_EXIT, hit, container, adjacent, -1, nullptr);
-    if (have_rec) {
-      const double* rec = sv.node(hit);
-      const V3 lp = map_point(rec + kNodeW2L, ph.p);
-      const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), rec + kNodeParams, lp);
-      const V3 nw = map_vector(rec + kNodeL2W, nl);
-      double c = fabs(dot(nw, ph.d));
-      if (c > 1.0) c = 1.0;
-      tally<P>(sv, T, ph, PVT_REC_EXIT, hit, &nw, lp, acos(c));
-    }
-    return false;
-  }
+  if (nh.hit == H.root_id) return kExit;
 
   // Beer-Lambert free path in the container (material.py:17-47 == :746-760)
-  const int c0 = sv.node_int(container, NI_COMP_START), cn = sv.node_int(container, NI_COMP_COUNT);
+  const int c0 = sv.node_int(nh.container, NI_COMP_START), cn = sv.node_int(nh.container, NI_COMP_COUNT);
   double alpha = 0.0;
   for (int k = 0; k < cn; ++k) alpha += absorption_at(sv, c0 + k, ph.wl);
-  double depth = PVT_INF;
-  if (alpha > kAlphaZero) depth = -log(1.0 - ph.rng.next()) / alpha;
-
-  if (depth < t0) {  // absorbed in the volume, :762-832
-    advance(ph, depth, n_container);
-    const double target = ph.rng.next() * alpha;
-    double running = 0.0;
-    int comp = c0;
-    for (int k = 0; k < cn; ++k) {
-      running += absorption_at(sv, c0 + k, ph.wl);
-      if (target <= running) { comp = c0 + k; break; }
-    }
-    log_event(L, sp.max_events, ph, PVT_EV_ABSORB, -1, container, -1, comp, nullptr);
-    const double* cr = sv.comp(comp);
-    const int ctype = sv.comp_int(comp, CI_TYPE);
-    if ((ctype == PVT_COMP_SCATTERER || ctype == PVT_COMP_LUMINOPHORE) && ph.rng.next() < cr[kCompQy]) {
-      ph.d = phase_direction(sv.comp_int(comp, CI_PHASE), cr[kCompPhaseParam], ph.rng);
-      ph.source = comp;
-      if (ctype == PVT_COMP_LUMINOPHORE) {  // component.py:381-440 == :795-812
-        const int es = sv.comp_int(comp, CI_EMS_START), en = sv.comp_int(comp, CI_EMS_N);
-        const double* ex = sv.w + H.off_ems_x + es;
-        const double* ec = sv.w + H.off_ems_cdf + es;
-        double p1 = 0.0;
-        if (sp.emit_method != PVT_EMIT_FULL) {
-          double nm = ph.wl;
-          if (sp.emit_method == PVT_EMIT_KT) nm = 1240.0 / (1240.0 / nm + 1.5 * kBoltzmannEv * 300.0);
-          p1 = interp_hinted(nm, ex, ec, en, cr[kCompEmsInvDx]);
-        }
-        const double gamma = p1 + (1.0 - p1) * ph.rng.next();
-        ph.wl = interp(gamma, ec, ex, en);
-        if (cr[kCompTauRad] > 0.0) ph.duration += -log(1.0 - ph.rng.next()) * cr[kCompTauRad];
-        log_event(L, sp.max_events, ph, PVT_EV_EMIT, -1, container, -1, comp, nullptr);
-      } else {
-        log_event(L, sp.max_events, ph, PVT_EV_SCATTER, -1, container, -1, comp, nullptr);
-      }
-      return true;
-    }
-    if (cr[kCompTauNr] > 0.0) ph.duration += -log(1.0 - ph.rng.next()) * cr[kCompTauNr];
-    int sel;
-    if (ctype == PVT_COMP_REACTOR) {
-      log_event(L, sp.max_events, ph, PVT_EV_REACT, -1, container, -1, comp, nullptr);
-      sel = PVT_REC_REACTED;
+  plan.alpha = alpha;
+  if (alpha > kAlphaZero) {
+    double ud;
+    if (Rng::kAddressed) {
+      rng.pair(kBlockPath, ud, plan.u);
     } else {
-      log_event(L, sp.max_events, ph, PVT_EV_NONRADIATIVE, -1, container, -1, comp, nullptr);
-      sel = PVT_REC_LOST;
+      ud = rng.one(kBlockPath, 0);
     }
-    if (have_rec) {
-      const V3 lp = map_point(sv.node(container) + kNodeW2L, ph.p);
-      tally<P>(sv, T, ph, sel, container, nullptr, lp, 0.0);
+    const double depth = -log(1.0 - ud) / alpha;
+    if (depth < nh.t0) {
+      plan.t = depth;
+      return kVolume;
     }
-    return false;
+  } else if (Rng::kAddressed) {
+    plan.u = rng.one(kBlockPath, 1);
   }
+  return kSurface;
+}
 
-  // reaches the surface, :834-895
-  advance(ph, t0, n_container);
+// Leaves the scene through the root boundary (:728-744).
+template <class P>
+__device__ __forceinline__ void exit_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
+                                          const StepParams& sp, P& ph, LaneStats& st, const StepPlan& plan) {
+  const int hit = plan.hit;
+  advance(ph, plan.t, sv.node(plan.container)[kNodeIndex]);
+  ++st.events;
+  PVT_LOG(ph, PVT_EV_EXIT, hit, plan.container, plan.adjacent, -1, nullptr);
+  if (sv.hdr().n_recorders > 0) {
+    const double* rec = sv.node(hit);
+    const V3 lp = map_point(rec + kNodeW2L, ph.p);
+    const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), rec + kNodeParams, lp);
+    const V3 nw = map_vector(rec + kNodeL2W, nl);
+    double c = fabs(dot(nw, ph.d));
+    if (c > 1.0) c = 1.0;
+    tally(sv, T, ph, PVT_REC_EXIT, hit, true, nw, lp, c);
+  }
+}
+
+// Absorbed in the volume (:762-832).  Returns true while the photon lives (re-emitted or scattered).
+template <class Rng, class P>
+__device__ __forceinline__ bool volume_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
+                                            const StepParams& sp, P& ph, Rng& rng, LaneStats& st, const StepPlan& plan) {
+  const Header& H = sv.hdr();
+  const int container = plan.container;
+  advance(ph, plan.t, sv.node(container)[kNodeIndex]);
+  const int c0 = sv.node_int(container, NI_COMP_START), cn = sv.node_int(container, NI_COMP_COUNT);
+  double u_target, u_yield;
+  if (Rng::kAddressed) rng.pair(kBlockAbsorb, u_target, u_yield);
+  else u_target = rng.one(kBlockAbsorb, 0);
+  const double target = u_target * plan.alpha;
+  double running = 0.0;
+  int comp = c0;
+  for (int k = 0; k < cn; ++k) {
+    running += absorption_at(sv, c0 + k, ph.wl);
+    if (target <= running) { comp = c0 + k; break; }
+  }
+  ++st.events;
+  PVT_LOG(ph, PVT_EV_ABSORB, -1, container, -1, comp, nullptr);
+  const double* cr = sv.comp(comp);
+  const int ctype = sv.comp_int(comp, CI_TYPE);
+  bool radiative = false;
+  if (ctype == PVT_COMP_SCATTERER || ctype == PVT_COMP_LUMINOPHORE) {
+    if (!Rng::kAddressed) u_yield = rng.one(kBlockAbsorb, 1);
+    radiative = u_yield < cr[kCompQy];
+  }
+  if (radiative) {
+    double g1, g2;
+    rng.pair(kBlockPhase, g1, g2);
+    ph.d = phase_direction(sv.comp_int(comp, CI_PHASE), cr[kCompPhaseParam], g1, g2);
+    ph.source = comp;
+    ++st.events;
+    if (ctype == PVT_COMP_LUMINOPHORE) {  // component.py:381-440 == :795-812
+      const int es = sv.comp_int(comp, CI_EMS_START), en = sv.comp_int(comp, CI_EMS_N);
+      const double* ex = sv.w + H.off_ems_x + es;
+      const double* ec = sv.w + H.off_ems_cdf + es;
+      double p1 = 0.0;
+      if (sp.emit_method != PVT_EMIT_FULL) {
+        double nm = ph.wl;
+        if (sp.emit_method == PVT_EMIT_KT) nm = 1240.0 / (1240.0 / nm + 1.5 * kBoltzmannEv * 300.0);
+        p1 = interp_hinted(nm, ex, ec, en, cr[kCompEmsInvDx]);
+      }
+      double u_gamma, u_delay;
+      if (Rng::kAddressed) rng.pair(kBlockEmit, u_gamma, u_delay);
+      else u_gamma = rng.one(kBlockEmit, 0);
+      const double gamma = p1 + (1.0 - p1) * u_gamma;
+      ph.wl = interp(gamma, ec, ex, en);
+      if (cr[kCompTauRad] > 0.0) {
+        if (!Rng::kAddressed) u_delay = rng.one(kBlockEmit, 1);
+        ph.duration += -log(1.0 - u_delay) * cr[kCompTauRad];
+      }
+      PVT_LOG(ph, PVT_EV_EMIT, -1, container, -1, comp, nullptr);
+    } else {
+      PVT_LOG(ph, PVT_EV_SCATTER, -1, container, -1, comp, nullptr);
+    }
+    return true;
+  }
+  if (cr[kCompTauNr] > 0.0) ph.duration += -log(1.0 - rng.one(kBlockEmit, 1)) * cr[kCompTauNr];
+  ++st.events;
+  int sel;
+  if (ctype == PVT_COMP_REACTOR) {
+    PVT_LOG(ph, PVT_EV_REACT, -1, container, -1, comp, nullptr);
+    sel = PVT_REC_REACTED;
+  } else {
+    PVT_LOG(ph, PVT_EV_NONRADIATIVE, -1, container, -1, comp, nullptr);
+    sel = PVT_REC_LOST;
+  }
+  if (H.n_recorders > 0) {
+    const V3 lp = map_point(sv.node(container) + kNodeW2L, ph.p);
+    tally(sv, T, ph, sel, container, false, V3{0.0, 0.0, 0.0}, lp, 1.0);
+  }
+  return false;
+}
+
+// Reaches a surface that is not the root boundary (:834-895).  Returns true while the photon lives.
+template <class Rng, class P>
+__device__ __forceinline__ bool surface_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
+                                             const StepParams& sp, P& ph, Rng& rng, LaneStats& st, const StepPlan& plan) {
+  const int hit = plan.hit, container = plan.container, adjacent = plan.adjacent;
+  const double n1 = sv.node(container)[kNodeIndex];
+  advance(ph, plan.t, n1);
+  ++st.events;
   if (adjacent < 0) {
-    log_event(L, sp.max_events, ph, PVT_EV_KILL, hit, container, -1, -1, nullptr);
+    PVT_LOG(ph, PVT_EV_KILL, hit, container, -1, -1, nullptr);
     return false;
   }
   const double* hrec = sv.node(hit);
@@ -318,12 +394,11 @@ __device__ __forceinline__ bool step_photon(const SceneView& sv, const TallySink
   const V3 nw = map_vector(hrec + kNodeL2W, nl);
   V3 nf = nw;
   if (dot(nf, ph.d) < 0.0) nf = neg(nf);
-  double c = dot(nf, ph.d);
+  double c = dot(nf, ph.d);  // cosine of the incidence angle, in [0, 1] up to rounding
   c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
-  const double angle = acos(c);
 
   const bool fresnel = sv.node_int(hit, NI_SURF) == PVT_SURF_FRESNEL;
-  const double n1 = n_container, n2 = sv.node(adjacent)[kNodeIndex];
+  const double n2 = sv.node(adjacent)[kNodeIndex];
   double R = 0.0;
   bool straight = false, lambert = false, fixed_R = false;
   const int facet = find_facet(sv, hit, nl);
@@ -334,70 +409,91 @@ __device__ __forceinline__ bool step_photon(const SceneView& sv, const TallySink
     const double fr = sv.facet(facet)[kFacetRefl];
     if (fr >= 0.0) { R = fr; fixed_R = true; }
   }
-  if (!fixed_R && fresnel) R = fresnel_R(angle, n1, n2);
+  if (!fixed_R && fresnel) R = fresnel_R_cos(c, n1, n2);
 
   double u = 1.0;
-  if (R > 0.0) u = ph.rng.next();  // surface.py:231-240: no draw when R == 0
+  if (R > 0.0) u = Rng::kAddressed ? plan.u : rng.one(kBlockPath, 1);  // surface.py:231-240: no draw when R == 0
+  int sel;
+  bool record = sv.hdr().n_recorders > 0;
   if (u < R) {
-    ph.d = lambert ? lambert_about(neg(nf), ph.rng) : mirror(ph.d, nw);
-    log_event(L, sp.max_events, ph, PVT_EV_REFLECT, hit, container, adjacent, -1, &nw);
-    if (have_rec && container != hit) tally<P>(sv, T, ph, PVT_REC_REFLECTED, hit, &nw, lp, angle);
+    if (lambert) {
+      double p1, p2;
+      rng.pair(kBlockLambert, p1, p2);
+      ph.d = lambert_about(neg(nf), p1, p2);
+    } else {
+      ph.d = mirror(ph.d, nw);
+    }
+    PVT_LOG(ph, PVT_EV_REFLECT, hit, container, adjacent, -1, &nw);
+    sel = PVT_REC_REFLECTED;
+    record = record && container != hit;
   } else {
     if (fresnel && !straight) ph.d = snell(ph.d, nf, n1, n2);
-    log_event(L, sp.max_events, ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, &nw);
-    if (have_rec) tally<P>(sv, T, ph, container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING, hit, &nw, lp, angle);
+    PVT_LOG(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, &nw);
+    sel = container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING;
   }
+  if (record) tally(sv, T, ph, sel, hit, true, nw, lp, c);
   return true;
 }
 
 // ---- on-device emission of the built-in light delegates (emit.py:22-134; scene.py:141-151) ---------------
-// Draw k of Philox stream kStreamEmit of ray id: k=0 wavelength, k=1..3 position, k=4,5 direction.
+// Uniform k of Philox stream kStreamEmit of ray id: k=0 wavelength, k=1..3 position, k=4,5 direction.
 __device__ __forceinline__ void emit_ray(const SceneView& sv, u64 id, long long index, V3& pos, V3& dir, double& wl) {
   const Header& H = sv.hdr();
   const int l = (int)(index % H.n_lights);
   const double* q = sv.light(l);
   V3 lp = V3{0.0, 0.0, 0.0}, ld = V3{0.0, 0.0, 1.0};
-  const U4 b0 = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), 0u, kStreamEmit}, kPhiloxKey0, kPhiloxKey1);
-  const U4 b1 = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), 1u, kStreamEmit}, kPhiloxKey0, kPhiloxKey1);
-  const U4 b2 = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), 2u, kStreamEmit}, kPhiloxKey0, kPhiloxKey1);
-  const double k0 = u53(b0.x, b0.y), k1 = u53(b0.z, b0.w), k2 = u53(b1.x, b1.y), k3 = u53(b1.z, b1.w);
-  const double u0 = u53(b2.x, b2.y), u1 = u53(b2.z, b2.w);
-  if (sv.light_int(l, LI_WL) == PVT_LWL_SPECTRUM) {
-    const int s = sv.light_int(l, LI_WL_START), n = sv.light_int(l, LI_WL_N);
-    wl = interp(k0, sv.w + H.off_wl_cdf + s, sv.w + H.off_wl_x + s, n);
-  } else {
-    wl = q[kLightWl];
-  }
-  const double px = q[kLightPos], py = q[kLightPos + 1], pz = q[kLightPos + 2];
-  switch (sv.light_int(l, LI_POS)) {
-    case PVT_LPOS_RECT:
-      lp.x = -px + (px - -px) * k1; lp.y = -py + (py - -py) * k2;
-      break;
-    case PVT_LPOS_CIRCLE: {
-      double s, c;
-      sincos(kTwoPi * k1, &s, &c);
-      const double r = sqrt(k2) * px;
-      lp.x = r * c; lp.y = r * s;
-    } break;
-    case PVT_LPOS_CUBE:
-      lp.x = -px + (px - -px) * k1; lp.y = -py + (py - -py) * k2; lp.z = -pz + (pz - -pz) * k3;
-      break;
-    default: break;
-  }
-  const double prm = q[kLightDir];
+  const int wl_kind = sv.light_int(l, LI_WL), pos_kind = sv.light_int(l, LI_POS);
   int kind = sv.light_int(l, LI_DIR);
+  if (wl_kind == PVT_LWL_SPECTRUM || pos_kind != PVT_LPOS_POINT) {
+    const U4 b0 = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), 0u, kStreamEmit}, kPhiloxKey0, kPhiloxKey1);
+    const U4 b1 = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), 1u, kStreamEmit}, kPhiloxKey0, kPhiloxKey1);
+    const double k0 = u53(b0.x, b0.y), k1 = u53(b0.z, b0.w), k2 = u53(b1.x, b1.y), k3 = u53(b1.z, b1.w);
+    if (wl_kind == PVT_LWL_SPECTRUM) {
+      const int s = sv.light_int(l, LI_WL_START), n = sv.light_int(l, LI_WL_N);
+      wl = interp(k0, sv.w + H.off_wl_cdf + s, sv.w + H.off_wl_x + s, n);
+    }
+    const double px = q[kLightPos], py = q[kLightPos + 1], pz = q[kLightPos + 2];
+    switch (pos_kind) {
+      case PVT_LPOS_RECT:
+        lp.x = -px + (px - -px) * k1; lp.y = -py + (py - -py) * k2;
+        break;
+      case PVT_LPOS_CIRCLE: {
+        double s, c;
+        sincospi(2.0 * k1, &s, &c);
+        const double r = sqrt(k2) * px;
+        lp.x = r * c; lp.y = r * s;
+      } break;
+      case PVT_LPOS_CUBE:
+        lp.x = -px + (px - -px) * k1; lp.y = -py + (py - -py) * k2; lp.z = -pz + (pz - -pz) * k3;
+        break;
+      default: break;
+    }
+  }
+  if (wl_kind != PVT_LWL_SPECTRUM) wl = q[kLightWl];
+  const double prm = q[kLightDir];
   if (kind == PVT_LDIR_HG && fabs(prm) < 1e-12) kind = PVT_LDIR_ISOTROPIC;
-  switch (kind) {
-    case PVT_LDIR_CONE: ld = polar(asin(sqrt(u0) * sin(prm)), kTwoPi * u1); break;
-    case PVT_LDIR_ISOTROPIC: ld = polar(acos(2.0 * u1 - 1.0), kTwoPi * u0); break;
-    case PVT_LDIR_LAMBERTIAN: ld = polar(asin(sqrt(u0)), kTwoPi * u1); break;
-    case PVT_LDIR_HG: {
-      const double s = 2.0 * u0 - 1.0;
-      const double f = (1.0 - prm * prm) / (1.0 + prm * s);
-      const double mu = (1.0 + prm * prm - f * f) / (2.0 * prm);
-      ld = polar(acos(mu), kTwoPi * u1);
-    } break;
-    default: break;
+  if (kind != PVT_LDIR_Z) {
+    const U4 b2 = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), 2u, kStreamEmit}, kPhiloxKey0, kPhiloxKey1);
+    const double u0 = u53(b2.x, b2.y), u1 = u53(b2.z, b2.w);
+    switch (kind) {
+      case PVT_LDIR_CONE: {
+        const double st = sqrt(u0) * sin(prm);
+        ld = polar_sc(st, sqrt(fmax(1.0 - st * st, 0.0)), u1);
+      } break;
+      case PVT_LDIR_ISOTROPIC: {
+        const double mu = 2.0 * u1 - 1.0;
+        ld = polar_sc(sqrt(fmax(1.0 - mu * mu, 0.0)), mu, u0);
+      } break;
+      case PVT_LDIR_LAMBERTIAN: ld = polar_sc(sqrt(u0), sqrt(fmax(1.0 - u0, 0.0)), u1); break;
+      case PVT_LDIR_HG: {
+        const double s = 2.0 * u0 - 1.0;
+        const double f = (1.0 - prm * prm) / (1.0 + prm * s);
+        double mu = (1.0 + prm * prm - f * f) / (2.0 * prm);
+        mu = mu > 1.0 ? 1.0 : (mu < -1.0 ? -1.0 : mu);
+        ld = polar_sc(sqrt(1.0 - mu * mu), mu, u1);
+      } break;
+      default: break;
+    }
   }
   pos = map_point(q + kLightL2W, lp);
   dir = map_vector(q + kLightL2W, ld);

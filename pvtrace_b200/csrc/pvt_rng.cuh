@@ -1,8 +1,8 @@
 // pvt_rng.cuh -- per-photon random streams.
 //
 //   Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), counter
-//   based: counter = (ray id lo, ray id hi, block, stream), fixed key.  One block gives two 53-bit uniforms, so
-//   draw k of a ray lives in block k/2 -- random access, nothing to store but the draw index.  The ray id is
+//   based: counter = (ray id lo, ray id hi, block, stream), fixed key.  One block gives two 53-bit uniforms.
+//   Nothing is stored per photon but its id and step number (see "Draw addressing" below).  The ray id is
 //   seed + first_index + i, the reference's per-ray seed (pvtrace/engine/_kernel.pyx:1090), which keeps the
 //   reference's "bundles with consecutive seed offsets concatenate exactly" contract (api.py:252-262).
 //
@@ -42,27 +42,52 @@ __host__ __device__ __forceinline__ double u53(uint32_t lo, uint32_t hi) {
   return (double)(v >> 11) * (1.0 / 9007199254740992.0);
 }
 
-// draw number k of stream `stream` of ray `id`
+// uniform number k of stream `stream` of ray `id` (random access): block k/2, half k%2
 __host__ __device__ __forceinline__ double philox_uniform_at(uint64_t id, uint32_t stream, uint32_t k) {
   const U4 r = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), k >> 1, stream}, kPhiloxKey0, kPhiloxKey1);
   return (k & 1u) ? u53(r.z, r.w) : u53(r.x, r.y);
 }
 
-struct PhiloxStream {
-  uint64_t id;
-  uint32_t k;     // next draw index
-  double spare;   // second uniform of the current block, valid when k is odd
-  __device__ __forceinline__ void init(uint64_t ray_id) { id = ray_id; k = 0; spare = 0.0; }
-  __device__ __forceinline__ double next() {
-    if (k & 1u) { ++k; return spare; }
-    const U4 r = philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), k >> 1, kStreamTrace}, kPhiloxKey0, kPhiloxKey1);
-    ++k;
-    spare = u53(r.z, r.w);
-    return u53(r.x, r.y);
-  }
+// Draw addressing of the tracer.  Every random decision of a photon step has a fixed address
+//   (photon id, step number, block, half)  ->  Philox counter (id_lo, id_hi, step * 8 + block, kStreamTrace)
+// so a draw never depends on how many draws came before it: stages of the wavefront kernel can fetch their
+// uniforms independently, and a skipped draw (e.g. no surface draw when the reflectivity is exactly zero,
+// pvtrace/material/surface.py:231-240) does not shift the stream of the rays that follow.
+enum {
+  kBlockPath = 0,     // half 0: Beer-Lambert free path            half 1: surface reflect / transmit test
+  kBlockAbsorb = 1,   // half 0: which component absorbs           half 1: quantum-yield test
+  kBlockPhase = 2,    // both halves: phase-function direction
+  kBlockEmit = 3,     // half 0: emission wavelength (gamma)       half 1: radiative / non-radiative delay
+  kBlockLambert = 4,  // both halves: Lambertian reflection
+  kBlocksPerStep = 8
 };
 
+struct PhiloxStream {
+  static constexpr bool kAddressed = true;  // draws are fetched by address, in any order
+  uint64_t id;
+  uint32_t step;  // 1-based trace-loop iteration of the photon (the reference's `count`)
+  uint32_t k;     // sequential cursor, used only by next() (known-answer exports)
+  __device__ __forceinline__ void init(uint64_t ray_id) { id = ray_id; step = 0; k = 0; }
+  __device__ __forceinline__ void begin_step(uint32_t count) { step = count; }
+  __device__ __forceinline__ U4 block(uint32_t b) const {
+    return philox4x32_10(U4{(uint32_t)id, (uint32_t)(id >> 32), step * kBlocksPerStep + b, kStreamTrace}, kPhiloxKey0,
+                         kPhiloxKey1);
+  }
+  __device__ __forceinline__ double one(uint32_t b, uint32_t half) {
+    const U4 r = block(b);
+    return half ? u53(r.z, r.w) : u53(r.x, r.y);
+  }
+  __device__ __forceinline__ void pair(uint32_t b, double& u0, double& u1) {
+    const U4 r = block(b);
+    u0 = u53(r.x, r.y);
+    u1 = u53(r.z, r.w);
+  }
+  __device__ __forceinline__ double next() { return philox_uniform_at(id, kStreamTrace, k++); }
+};
+
+// The reference's generator: draws are consumed in program order, addresses are ignored.
 struct XoshiroStream {
+  static constexpr bool kAddressed = false;  // draws must be consumed in the reference's program order
   uint64_t s0, s1, s2, s3;
   __device__ __forceinline__ static uint64_t splitmix(uint64_t& x) {
     uint64_t z = (x += 0x9E3779B97F4A7C15ull);
@@ -74,6 +99,7 @@ struct XoshiroStream {
     uint64_t x = ray_id;
     s0 = splitmix(x); s1 = splitmix(x); s2 = splitmix(x); s3 = splitmix(x);
   }
+  __device__ __forceinline__ void begin_step(uint32_t) {}
   __device__ __forceinline__ double next() {
     const uint64_t result = s0 + s3;
     const uint64_t t = s1 << 17;
@@ -81,6 +107,8 @@ struct XoshiroStream {
     s3 = (s3 << 45) | (s3 >> 19);
     return (double)(result >> 11) * (1.0 / 9007199254740992.0);
   }
+  __device__ __forceinline__ double one(uint32_t, uint32_t) { return next(); }
+  __device__ __forceinline__ void pair(uint32_t, double& u0, double& u1) { u0 = next(); u1 = next(); }
 };
 
 }  // namespace pvt

@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get(
     "PVTRACE_B200_LIB", os.path.join(os.path.dirname(HERE), "csrc", "libpvtrace_b200.so"))
 
+FLAG_REGISTER_KERNEL = 1  # PVT_FLAG_REGISTER_KERNEL: force the one-photon-per-lane kernel
 RNG_PHILOX, RNG_XOSHIRO = 0, 1
 RNG_MODES = {"philox": RNG_PHILOX, "xoshiro": RNG_XOSHIRO}
 NSTATS = 8
@@ -133,11 +134,11 @@ def marshal_emitter(emitter):
 
 
 def make_params(n, seed, maxsteps, max_events, emit_method, record_every, first_index=0, rng_mode=RNG_PHILOX,
-                device=0):
+                device=0, flags=0):
     p = PvtParams()
     p.n, p.first_index, p.seed = int(n), int(first_index), int(seed) & 0xFFFFFFFFFFFFFFFF
     p.record_every, p.maxsteps, p.max_events = int(record_every), int(maxsteps), int(max_events)
-    p.emit_method, p.rng_mode, p.device, p.flags = int(emit_method), int(rng_mode), int(device), 0
+    p.emit_method, p.rng_mode, p.device, p.flags = int(emit_method), int(rng_mode), int(device), int(flags)
     return p
 
 
@@ -256,7 +257,7 @@ def _vp(array):
 
 def trace_bundle(compiled, positions, directions, wavelengths, seed, maxsteps, max_events, emit_method,
                  num_threads=0, record_every=1, *, emitter=None, n=None, first_index=0, rng_mode=RNG_PHILOX,
-                 device=0, return_elapsed=False):
+                 device=0, return_elapsed=False, flags=0):
     """Drop-in for pvtrace.engine._kernel.trace_bundle (pvtrace/engine/_kernel.pyx:903-1115).
 
     `num_threads` is accepted for signature compatibility and ignored (the device schedules itself).  With an
@@ -277,7 +278,8 @@ def trace_bundle(compiled, positions, directions, wavelengths, seed, maxsteps, m
     if emitter is not None:
         emit_struct, keep_e = marshal_emitter(emitter)
         keep += keep_e
-    params = make_params(n, seed, maxsteps, max_events, emit_method, record_every, first_index, rng_mode, device)
+    params = make_params(n, seed, maxsteps, max_events, emit_method, record_every, first_index, rng_mode, device,
+                         flags)
     data, out = allocate_outputs(compiled, n, max_events, record_every)
     elapsed = C.c_double(0.0)
     status = lib.pvt_trace_bundle(C.byref(scene), C.byref(emit_struct) if emit_struct is not None else None,
@@ -330,10 +332,10 @@ class Context:
         check(self._lib.pvt_context_reset(self._handle, C.c_void_p(stream)), "pvt_context_reset")
 
     def trace(self, n, seed, *, d_positions=0, d_directions=0, d_wavelengths=0, first_index=0, maxsteps=1000,
-              max_events=128, emit_method=0, record_every=0, rng_mode=RNG_PHILOX, stream=0):
+              max_events=128, emit_method=0, record_every=0, rng_mode=RNG_PHILOX, stream=0, flags=0):
         """Enqueue one bundle (asynchronous).  Null ray pointers => rays come from the context's emitter."""
         params = make_params(n, seed, maxsteps, max_events, emit_method, record_every, first_index, rng_mode,
-                             self.device)
+                             self.device, flags)
         self._last = (int(n), int(max_events), int(record_every))
         status = self._lib.pvt_trace_device(self._handle, C.c_void_p(d_positions), C.c_void_p(d_directions),
                                             C.c_void_p(d_wavelengths), C.byref(params), C.c_void_p(stream))
