@@ -50,6 +50,7 @@ struct pvt_context {
   DeviceBuffer<u64> slabs;  // CTA-private tally slabs of one launch: [max_grid][10 R]
   int max_grid = 0;
   int wave_threads = 0;     // CTA size of the wavefront kernel for this scene, 0: scene needs trace_kernel
+  int wave_ctas = 1;        // resident CTAs per SM
   size_t wave_smem = 0;
   // event log of the last trace
   long long log_rows = 0, log_rays = 0;
@@ -108,10 +109,27 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
   return 0;
 }
 
+struct WaveVariant { int threads, ctas; };
+constexpr int kWaveVariants = 8;
+static const WaveVariant kWaveTable[kWaveVariants] = {{1024, 1}, {768, 1}, {512, 2}, {512, 1}, {384, 2}, {256, 4}, {256, 3}, {256, 2}};
+
 template <class K>
 static int wave_attr(K kernel, size_t smem) {
   PVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return 0;
+}
+
+// launches (or, with args == nullptr, only configures) the wavefront variant chosen for the context
+#define PVT_WAVE_CASE(T, B)                                                                      \
+  if (c->wave_threads == T && c->wave_ctas == B) {                                               \
+    if (!args) return wave_attr(wavefront_kernel<T, B>, c->wave_smem);                           \
+    wavefront_kernel<T, B><<<grid, T, c->wave_smem, st>>>(*args);                                \
+    return 0;                                                                                    \
+  }
+static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
+  PVT_WAVE_CASE(1024, 1) PVT_WAVE_CASE(768, 1) PVT_WAVE_CASE(512, 2) PVT_WAVE_CASE(512, 1)
+  PVT_WAVE_CASE(384, 2) PVT_WAVE_CASE(256, 4) PVT_WAVE_CASE(256, 3) PVT_WAVE_CASE(256, 2)
+  return fail("no wavefront kernel variant for %d threads x %d CTAs", c->wave_threads, c->wave_ctas);
 }
 
 extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context_t** out) {
@@ -141,14 +159,17 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   // wavefront kernel: needs the blob AND the photon pool in shared memory, <= 64 recorders (seen mask), <= 254 nodes
   c->wave_threads = 0;
   if (c->R() <= 64) {
-    int prefer = 1024;
-    if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) prefer = atoi(env);
-    const int choices[3] = {1024, 768, 512};
-    for (int k = 0; k < 3 && prefer > 0; ++k) {
-      const int t = choices[k];
-      if (t > prefer) continue;
+    int want_t = 512, want_b = 2;
+    if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) want_t = atoi(env);
+    if (const char* env = getenv("PVT_WAVEFRONT_CTAS")) want_b = atoi(env);
+    for (int k = 0; k < kWaveVariants && want_t > 0; ++k) {
+      const int t = kWaveTable[k].threads, b = kWaveTable[k].ctas;
+      if (t > want_t || (t == want_t && b > want_b)) continue;  // table is ordered: largest first
       const size_t need = wavefront_smem_bytes(c->blob_words, t - 64);
-      if (need <= (size_t)prop.sharedMemPerBlockOptin) { c->wave_threads = t; c->wave_smem = need; break; }
+      if ((need + 1024) * b <= (size_t)prop.sharedMemPerMultiprocessor && need <= (size_t)prop.sharedMemPerBlockOptin) {
+        c->wave_threads = t; c->wave_ctas = b; c->wave_smem = need;
+        break;
+      }
     }
   }
 
@@ -166,9 +187,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   if (!rc) rc = occupancy(trace_kernel<PhiloxStream, 8>, c->smem_bytes, &c->blocks_per_sm[1]);
   if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 2>, c->smem_bytes, &c->blocks_per_sm[2]);
   if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 8>, c->smem_bytes, &c->blocks_per_sm[3]);
-  if (!rc && c->wave_threads == 1024) rc = wave_attr(wavefront_kernel<1024>, c->wave_smem);
-  if (!rc && c->wave_threads == 768) rc = wave_attr(wavefront_kernel<768>, c->wave_smem);
-  if (!rc && c->wave_threads == 512) rc = wave_attr(wavefront_kernel<512>, c->wave_smem);
+  if (!rc && c->wave_threads > 0) rc = launch_wave(c, nullptr, 0, 0);  // attribute setup only
   if (!rc && c->smem_bytes > 48 * 1024 &&
       cudaFuncSetAttribute(intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess)
     rc = fail("cudaFuncSetAttribute(intersect_kernel) failed");
@@ -278,14 +297,11 @@ extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const dou
     // one persistent CTA per SM, each owning a contiguous slice of the photon range
     const int pool = c->wave_threads - 64;
     const long long want_blocks = (P->n + pool - 1) / pool;
-    grid = (int)(want_blocks < c->sm_count ? want_blocks : c->sm_count);
-    if (P->n / grid >= (1ll << 31)) return fail("bundle too large: at most 2^31 rays per SM per call");
+    const long long resident = (long long)c->sm_count * c->wave_ctas;
+    grid = (int)(want_blocks < resident ? want_blocks : resident);
+    if (P->n / grid >= (1ll << 31)) return fail("bundle too large: at most 2^31 rays per resident CTA per call");
     PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
-    switch (c->wave_threads) {
-      case 1024: wavefront_kernel<1024><<<grid, 1024, c->wave_smem, st>>>(a); break;
-      case 768: wavefront_kernel<768><<<grid, 768, c->wave_smem, st>>>(a); break;
-      default: wavefront_kernel<512><<<grid, 512, c->wave_smem, st>>>(a); break;
-    }
+    PVT_TRY(launch_wave(c, &a, grid, st));
   } else {
     const int wide = c->R() > 64;
     const int which = (P->rng_mode == PVT_RNG_XOSHIRO ? 2 : 0) + wide;

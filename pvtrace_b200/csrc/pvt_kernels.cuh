@@ -116,13 +116,20 @@ __device__ __forceinline__ void retire_cta(const TraceArgs& a, int R, const Lane
   }
 }
 
+// Is ray i of the bundle sampled for the event log, and which recorded ray is it?  (64-bit division: out of line,
+// once per photon.)
+__device__ __noinline__ int sampled_ordinal(long long i, long long record_every) {
+  if (record_every <= 0 || i % record_every != 0) return -1;
+  return (int)(i / record_every);
+}
+
 // =========================================================================================================
 // wavefront_kernel
 
 // Shared-memory pool of P photon slots, structure of arrays.  kPoolDoubles double columns, then 64-bit, 32-bit
 // and 16-bit columns; column c of slot s is at base + c * P + s.
 constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
-constexpr int kPoolWords = 5;     // count (< 0: slot is empty), source, nlog (< 0: ray not sampled), idx, ids
+constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, idx, ids, log_ray (< 0: not sampled)
 __host__ __device__ constexpr size_t pool_bytes(int P) {
   return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + 64 /*counters*/;
 }
@@ -133,7 +140,7 @@ __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
 struct PoolView {
   double *px, *py, *pz, *dx, *dy, *dz, *wl, *trav, *dur, *t, *u, *alpha;
   u64* seen;
-  int32_t *count, *source, *nlog;
+  int32_t *count, *source, *nlog, *log_ray;
   uint32_t *idx, *ids;
   uint16_t *qv, *qs, *qe;
   uint32_t* counters;  // [2][4] queue lengths, double buffered by iteration parity; [8..9] next index of the slice
@@ -148,7 +155,8 @@ __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
   int32_t* w = reinterpret_cast<int32_t*>(d + 13 * P);
   v.count = w; v.source = w + P; v.nlog = w + 2 * P;
   v.idx = reinterpret_cast<uint32_t*>(w + 3 * P); v.ids = reinterpret_cast<uint32_t*>(w + 4 * P);
-  uint16_t* h = reinterpret_cast<uint16_t*>(w + 5 * P);
+  v.log_ray = w + 5 * P;
+  uint16_t* h = reinterpret_cast<uint16_t*>(w + 6 * P);
   v.qv = h; v.qs = h + P; v.qe = h + 2 * P;
   v.counters = reinterpret_cast<uint32_t*>(h + 3 * P);  // P is a multiple of 32: 4-byte aligned
   return v;
@@ -156,16 +164,15 @@ __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
 
 typedef PhotonT<2> PoolPhoton;
 
-__device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, long long slice_lo,
-                                          long long record_every, int max_events) {
+__device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, int max_events) {
   ph.p = V3{pool.px[s], pool.py[s], pool.pz[s]};
   ph.d = V3{pool.dx[s], pool.dy[s], pool.dz[s]};
   ph.wl = pool.wl[s]; ph.travelled = pool.trav[s]; ph.duration = pool.dur[s];
   ph.count = pool.count[s]; ph.source = pool.source[s]; ph.nlog = pool.nlog[s];
   const u64 seen = pool.seen[s];
   ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
-  ph.log_base = -1;
-  if (ph.nlog >= 0) ph.log_base = ((long long)pool.idx[s] + slice_lo) / record_every * (long long)max_events;
+  ph.log_ray = pool.log_ray[s];
+  ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * max_events;
 }
 __device__ __forceinline__ void store_slot(const PoolView& pool, int s, const PoolPhoton& ph) {
   pool.px[s] = ph.p.x; pool.py[s] = ph.p.y; pool.pz[s] = ph.p.z;
@@ -186,8 +193,8 @@ __device__ __forceinline__ void push_queue(uint16_t* q, uint32_t* counter, bool 
   if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)s;
 }
 
-template <int T>
-__global__ void __launch_bounds__(T, 1) wavefront_kernel(const TraceArgs a) {
+template <int T, int B>
+__global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
   constexpr int P = T - 64;  // two warps have no home slot: room for the warp padding of the queues in stage 2
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -236,23 +243,23 @@ __global__ void __launch_bounds__(T, 1) wavefront_kernel(const TraceArgs a) {
           } else {
             emit_ray(sv, id, a.first_index + i, ph.p, ph.d, ph.wl);
           }
-          ph.log_base = -1;
-          if (a.record_every > 0 && i % a.record_every == 0) ph.log_base = i / a.record_every * (long long)sp.max_events;
+          ph.log_ray = a.record_every > 0 ? sampled_ordinal(i, a.record_every) : -1;
+          ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
           begin_photon(ph, L, sp, st);
-          if (ph.log_base < 0) ph.nlog = -1;
           pool.idx[tid] = mine;
+          pool.log_ray[tid] = ph.log_ray;
           fresh = true;
         }
       }
       StepClass cls = kDead;
       if (fresh || !dead) {
-        if (!fresh) load_slot(pool, tid, ph, slice_lo, a.record_every, sp.max_events);
+        if (!fresh) load_slot(pool, tid, ph, sp.max_events);
         PhiloxStream rng = rng0;
         rng.id += (u64)(slice_lo + pool.idx[tid]);
         StepPlan plan;
         cls = classify_step(sv, sink, L, sp, ph, rng, st, plan);
         if (cls == kDead) {
-          if (ph.log_base >= 0) L.counts[ph.log_base / sp.max_events] = ph.nlog;
+          if (ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
           pool.count[tid] = -1;
         } else {
           if (fresh) store_slot(pool, tid, ph);
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(T, 1) wavefront_kernel(const TraceArgs a) {
     else if (tid - pv - ps < ce) { slot = pool.qe[tid - pv - ps]; cls = kExit; }
     if (slot >= 0) {
       PoolPhoton ph;
-      load_slot(pool, slot, ph, slice_lo, a.record_every, sp.max_events);
+      load_slot(pool, slot, ph, sp.max_events);
       PhiloxStream rng = rng0;
       rng.id += (u64)(slice_lo + pool.idx[slot]);
       rng.begin_step((uint32_t)ph.count);
@@ -289,14 +296,19 @@ __global__ void __launch_bounds__(T, 1) wavefront_kernel(const TraceArgs a) {
       plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
       if (plan.adjacent == 0xff) plan.adjacent = -1;
       bool alive;
-      if (cls == kVolume) alive = volume_step(sv, sink, L, sp, ph, rng, st, plan);
-      else if (cls == kSurface) alive = surface_step(sv, sink, L, sp, ph, rng, st, plan);
-      else { exit_step(sv, sink, L, sp, ph, st, plan); alive = false; }
+      TallyReq tr;
+      if (cls == kVolume) alive = volume_step(sv, L, sp, ph, rng, st, plan, tr);
+      else if (cls == kSurface) alive = surface_step(sv, L, sp, ph, rng, st, plan, tr);
+      else { exit_step(sv, L, sp, ph, st, plan, tr); alive = false; }
       if (alive) {
         store_slot(pool, slot, ph);
       } else {
-        if (ph.log_base >= 0) L.counts[ph.log_base / sp.max_events] = ph.nlog;
+        if (ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
         pool.count[slot] = -1;
+      }
+      if (tr.sel >= 0) {
+        tally(sv, sink, ph, tr);
+        if (alive) pool.seen[slot] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);
       }
     }
     __syncthreads();
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
   const unsigned lt_mask = (1u << lane) - 1u;
   PhotonT<SW> ph;
   Rng rng;
-  ph.log_base = -1; ph.nlog = 0;
+  ph.log_base = -1; ph.log_ray = -1; ph.nlog = 0;
   bool alive = false, exhausted = false;
   long long res_next = 0, res_end = 0;  // warp-uniform reservoir [res_next, res_end) of photon indices
   LaneStats st;
@@ -364,8 +376,8 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
             emit_ray(sv, id, a.first_index + idx, ph.p, ph.d, ph.wl);
           }
           rng.init(id);
-          ph.log_base = -1;
-          if (a.record_every > 0 && idx % a.record_every == 0) ph.log_base = (idx / a.record_every) * (long long)sp.max_events;
+          ph.log_ray = a.record_every > 0 ? sampled_ordinal(idx, a.record_every) : -1;
+          ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
           begin_photon(ph, L, sp, st);
           alive = true;
         } else {
@@ -377,15 +389,17 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
     if (alive) {
       StepPlan plan;
       const StepClass cls = classify_step(sv, sink, L, sp, ph, rng, st, plan);
-      if (cls == kVolume) alive = volume_step(sv, sink, L, sp, ph, rng, st, plan);
-      else if (cls == kSurface) alive = surface_step(sv, sink, L, sp, ph, rng, st, plan);
+      TallyReq tr;
+      if (cls == kVolume) alive = volume_step(sv, L, sp, ph, rng, st, plan, tr);
+      else if (cls == kSurface) alive = surface_step(sv, L, sp, ph, rng, st, plan, tr);
       else {
-        if (cls == kExit) exit_step(sv, sink, L, sp, ph, st, plan);
+        if (cls == kExit) exit_step(sv, L, sp, ph, st, plan, tr);
         alive = false;
       }
-      if (!alive && ph.log_base >= 0) {  // a sampled ray publishes its event count when it retires
-        L.counts[ph.log_base / sp.max_events] = ph.nlog;
-        ph.log_base = -1;
+      if (tr.sel >= 0) tally(sv, sink, ph, tr);
+      if (!alive && ph.log_ray >= 0) {  // a sampled ray publishes its event count when it retires
+        L.counts[ph.log_ray] = ph.nlog;
+        ph.log_ray = -1; ph.log_base = -1;
       }
     }
   }

@@ -48,7 +48,8 @@ struct PhotonT {
   V3 p, d;
   double wl, travelled, duration;
   int32_t source, count, nlog;
-  long long log_base;  // first log row of this ray, < 0 when the ray is not sampled
+  int32_t log_ray;     // ordinal of this ray among the recorded ones (index into counts), < 0: not sampled
+  long long log_base;  // first log row of this ray == log_ray * max_events, < 0 when the ray is not sampled
   uint32_t seen[kSeenWords];
 };
 
@@ -108,82 +109,137 @@ __device__ __forceinline__ double absorption_at(const SceneView& sv, int c, doub
   return interp_hinted(x, sv.w + h.off_abs_x + start, sv.w + h.off_abs_y + start, n, sv.comp(c)[kCompAbsInvDx]);
 }
 
-// ---- event log (_kernel.pyx:562-597).  Out of line: only sampled rays ever get here. ----------------------
+// ---- event log (_kernel.pyx:562-597).  Out of line and by value: only sampled rays ever get here. ----------
 
-template <class P>
-__device__ __noinline__ void log_event(const LogColumns& L, int max_events, P& ph, int kind, int hit, int container,
-                                       int adjacent, int component, const V3* normal) {
-  if (ph.nlog >= max_events) return;
-  const long long row = ph.log_base + ph.nlog;
+__device__ __noinline__ void log_event(const LogColumns& L, long long row, int kind, int hit, int container, int adjacent,
+                                       int component, int source, V3 p, V3 d, bool has_normal, V3 normal, double wl,
+                                       double travelled, double duration) {
   L.kind[row] = (uint8_t)kind;
   L.hit[row] = hit; L.container[row] = container; L.adjacent[row] = adjacent;
-  L.component[row] = component; L.source[row] = ph.source;
-  L.position[3 * row] = ph.p.x; L.position[3 * row + 1] = ph.p.y; L.position[3 * row + 2] = ph.p.z;
-  L.direction[3 * row] = ph.d.x; L.direction[3 * row + 1] = ph.d.y; L.direction[3 * row + 2] = ph.d.z;
-  if (normal) { L.normal[3 * row] = normal->x; L.normal[3 * row + 1] = normal->y; L.normal[3 * row + 2] = normal->z; }
-  L.wavelength[row] = ph.wl; L.travelled[row] = ph.travelled; L.duration[row] = ph.duration;
-  ++ph.nlog;
+  L.component[row] = component; L.source[row] = source;
+  L.position[3 * row] = p.x; L.position[3 * row + 1] = p.y; L.position[3 * row + 2] = p.z;
+  L.direction[3 * row] = d.x; L.direction[3 * row + 1] = d.y; L.direction[3 * row + 2] = d.z;
+  if (has_normal) { L.normal[3 * row] = normal.x; L.normal[3 * row + 1] = normal.y; L.normal[3 * row + 2] = normal.z; }
+  L.wavelength[row] = wl; L.travelled[row] = travelled; L.duration[row] = duration;
 }
-#define PVT_LOG(ph, ...) do { if ((ph).log_base >= 0) log_event(L, sp.max_events, ph, __VA_ARGS__); } while (0)
+// log one event of photon `ph` if the ray is sampled and has budget left
+#define PVT_LOG_N(ph, kind, hit, cont, adj, comp, has_n, nrm)                                                          \
+  do {                                                                                                                 \
+    if ((ph).log_base >= 0 && (ph).nlog < sp.max_events) {                                                             \
+      log_event(L, (ph).log_base + (ph).nlog, kind, hit, cont, adj, comp, (ph).source, (ph).p, (ph).d, has_n, nrm,     \
+                (ph).wl, (ph).travelled, (ph).duration);                                                               \
+      ++(ph).nlog;                                                                                                     \
+    }                                                                                                                  \
+  } while (0)
+#define PVT_LOG(ph, kind, hit, cont, adj, comp) PVT_LOG_N(ph, kind, hit, cont, adj, comp, false, (V3{0.0, 0.0, 0.0}))
 
 // ---- tallies (_kernel.pyx:501-556; semantics restated by engine/tally.py:26-47,86-156) -------------------
 
-__device__ __forceinline__ double ray_property(int prop, double wl, double angle, double duration, double travelled,
-                                               const V3& lp) {
-  switch (prop) {
-    case 0: return wl;
-    case 1: return angle;
-    case 2: return duration;
-    case 3: return travelled;
-    case 4: return lp.x;
-    case 5: return lp.y;
-    default: return lp.z;
-  }
+// reductions into GLOBAL memory that return nothing (SASS RED): no round trip, no CAS loop
+__device__ __forceinline__ void red_add(u64* p, u64 v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
-// `cosine` is the cosine of the incidence angle (1 for volume events => angle 0); acos is taken only if a
-// recorder actually matches for the first time.
-template <class P>
-__device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, int sel, int node,
-                                      bool has_normal, const V3& wnormal, const V3& lp, double cosine) {
+__device__ __forceinline__ double ray_property(int prop, double wl, double angle, double duration, double travelled,
+                                               const V3& lp) {
+  double v = lp.z;
+  v = prop == 0 ? wl : v;
+  v = prop == 1 ? angle : v;
+  v = prop == 2 ? duration : v;
+  v = prop == 3 ? travelled : v;
+  v = prop == 4 ? lp.x : v;
+  v = prop == 5 ? lp.y : v;
+  return v;
+}
+
+template <int SW>
+struct SeenMask {
+  uint32_t w[SW];
+};
+
+// One copy of the recorder loop for the whole kernel (every stage calls it warp-convergently).  `cosine` is the
+// cosine of the incidence angle (1 for volume events => angle 0); acos is taken only when a recorder matches for
+// the first time.  Returns the updated distinct-ray mask.
+template <int SW>
+__device__ __noinline__ SeenMask<SW> tally_event(const SceneView sv, const TallySink T, SeenMask<SW> seen, int sel,
+                                                 int node, bool has_normal, V3 wnormal, V3 lp, double cosine, double wl,
+                                                 double duration, double travelled) {
   const int R = sv.hdr().n_recorders;
   double angle = -1.0;
-  for (int r = 0; r < R; ++r) {
-    if (sv.rec_int(r, RI_NODE) != node || sv.rec_int(r, RI_EVENT) != sel) continue;
-    const double* q = sv.rec(r);
-    if (sv.rec_int(r, RI_HAS_FACET)) {
+  int r = -1;
+  for (;;) {
+    // next recorder matching (node, selector[, facet]); lanes search independently, then update together
+    for (++r; r < R; ++r) {
+      if (sv.rec_int(r, RI_NODE) != node || sv.rec_int(r, RI_EVENT) != sel) continue;
+      if (!sv.rec_int(r, RI_HAS_FACET)) break;
       if (!has_normal) continue;
+      const double* q = sv.rec(r);
       const double tol = q[kRecAtol];
-      if (fabs(q[0] - wnormal.x) > tol || fabs(q[1] - wnormal.y) > tol || fabs(q[2] - wnormal.z) > tol) continue;
+      if (fabs(q[0] - wnormal.x) <= tol && fabs(q[1] - wnormal.y) <= tol && fabs(q[2] - wnormal.z) <= tol) break;
     }
-    atomicAdd(&T.cross[r], 1ull);
+    if (r >= R) break;
+    red_add(&T.cross[r], 1ull);
     const uint32_t bit = 1u << (r & 31);
-    if (ph.seen[r >> 5] & bit) continue;
-    ph.seen[r >> 5] |= bit;
+    bool was_seen = false;
+#pragma unroll
+    for (int k = 0; k < SW; ++k)
+      if (k == (r >> 5)) { was_seen = (seen.w[k] & bit) != 0; seen.w[k] |= bit; }
+    if (was_seen) continue;
     if (angle < 0.0) angle = cosine >= 1.0 ? 0.0 : acos(cosine);
-    atomicAdd(&T.distinct[r], 1ull);
+    red_add(&T.distinct[r], 1ull);
     double* m = T.sums + 8 * r;
-    atomicAdd(m + 0, ph.wl);         atomicAdd(m + 1, ph.wl * ph.wl);
-    atomicAdd(m + 2, angle);         atomicAdd(m + 3, angle * angle);
-    atomicAdd(m + 4, ph.duration);   atomicAdd(m + 5, ph.duration * ph.duration);
-    atomicAdd(m + 6, ph.travelled);  atomicAdd(m + 7, ph.travelled * ph.travelled);
+    red_add(m + 0, wl);         red_add(m + 1, wl * wl);
+    red_add(m + 2, angle);      red_add(m + 3, angle * angle);
+    red_add(m + 4, duration);   red_add(m + 5, duration * duration);
+    red_add(m + 6, travelled);  red_add(m + 7, travelled * travelled);
     const int h0 = sv.rec_int(r, RI_HIST_START), h1 = h0 + sv.rec_int(r, RI_HIST_N);
     for (int h = h0; h < h1; ++h) {
       const double* g = sv.hist(h);
       const int na = sv.hist_int(h, HI_NA), nb = sv.hist_int(h, HI_NB), pb = sv.hist_int(h, HI_PROP_B);
-      const double va = ray_property(sv.hist_int(h, HI_PROP_A), ph.wl, angle, ph.duration, ph.travelled, lp);
+      const double va = ray_property(sv.hist_int(h, HI_PROP_A), wl, angle, duration, travelled, lp);
       const int ia = (int)((va - g[kHistLoA]) / (g[kHistHiA] - g[kHistLoA]) * na);
       if (ia < 0 || ia >= na) continue;
       int bin = ia;
       if (pb >= 0) {
-        const double vb = ray_property(pb, ph.wl, angle, ph.duration, ph.travelled, lp);
+        const double vb = ray_property(pb, wl, angle, duration, travelled, lp);
         const int ib = (int)((vb - g[kHistLoB]) / (g[kHistHiB] - g[kHistLoB]) * nb);
         if (ib < 0 || ib >= nb) continue;
         bin = ia * nb + ib;
       }
-      atomicAdd(&T.bins[sv.hist_int(h, HI_OFFSET) + bin], 1ull);
+      red_add(&T.bins[sv.hist_int(h, HI_OFFSET) + bin], 1ull);
     }
   }
+  return seen;
+}
+
+template <class P>
+__device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, int sel, int node,
+                                      bool has_normal, const V3& wnormal, const V3& lp, double cosine) {
+  constexpr int SW = (int)(sizeof(ph.seen) / 4);
+  SeenMask<SW> seen;
+#pragma unroll
+  for (int k = 0; k < SW; ++k) seen.w[k] = ph.seen[k];
+  seen = tally_event<SW>(sv, T, seen, sel, node, has_normal, wnormal, lp, cosine, ph.wl, ph.duration, ph.travelled);
+#pragma unroll
+  for (int k = 0; k < SW; ++k) ph.seen[k] = seen.w[k];
+}
+
+// A stage does not tally itself: it fills in a request and the kernel makes the (single, out-of-line) call once
+// the photon has been written back, when almost nothing is live in registers.
+struct TallyReq {
+  int sel = -1;  // PVT_REC_*, < 0: nothing to tally
+  int node;
+  bool has_normal;
+  V3 normal, lp;
+  double cosine;
+};
+
+template <class P>
+__device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, const TallyReq& tr) {
+  tally(sv, T, ph, tr.sel, tr.node, tr.has_normal, tr.normal, tr.lp, tr.cosine);
 }
 
 // facet-surface extension: first facet of `node` whose LOCAL normal equals nl within its tolerance
@@ -217,7 +273,7 @@ __device__ __forceinline__ void begin_photon(P& ph, const LogColumns& L, const S
 #pragma unroll
   for (int w = 0; w < (int)(sizeof(ph.seen) / 4); ++w) ph.seen[w] = 0u;
   ++st.rays; ++st.events;
-  PVT_LOG(ph, PVT_EV_GENERATE, -1, -1, -1, -1, nullptr);
+  PVT_LOG(ph, PVT_EV_GENERATE, -1, -1, -1, -1);
 }
 
 // What classify_step hands to the second stage
@@ -239,7 +295,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Ta
   // event budget of sampled rays: keep room for the KILL record (:658-663)
   if (ph.log_base >= 0 && ph.nlog >= sp.max_events - 1) {
     ++st.events;
-    PVT_LOG(ph, PVT_EV_KILL, -1, -1, -1, -1, nullptr);
+    PVT_LOG(ph, PVT_EV_KILL, -1, -1, -1, -1);
     return kDead;
   }
   ++st.steps;
@@ -250,7 +306,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Ta
 
   if (ph.count > sp.maxsteps) {  // :716-723
     ++st.events;
-    PVT_LOG(ph, PVT_EV_KILL, -1, nh.container, -1, -1, nullptr);
+    PVT_LOG(ph, PVT_EV_KILL, -1, nh.container, -1, -1);
     if (H.n_recorders > 0) {
       const V3 lp = map_point(sv.node(nh.container) + kNodeW2L, ph.p);
       tally(sv, T, ph, PVT_REC_KILLED, nh.container, false, V3{0.0, 0.0, 0.0}, lp, 1.0);
@@ -284,12 +340,12 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Ta
 
 // Leaves the scene through the root boundary (:728-744).
 template <class P>
-__device__ __forceinline__ void exit_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
-                                          const StepParams& sp, P& ph, LaneStats& st, const StepPlan& plan) {
+__device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
+                                          LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit;
   advance(ph, plan.t, sv.node(plan.container)[kNodeIndex]);
   ++st.events;
-  PVT_LOG(ph, PVT_EV_EXIT, hit, plan.container, plan.adjacent, -1, nullptr);
+  PVT_LOG(ph, PVT_EV_EXIT, hit, plan.container, plan.adjacent, -1);
   if (sv.hdr().n_recorders > 0) {
     const double* rec = sv.node(hit);
     const V3 lp = map_point(rec + kNodeW2L, ph.p);
@@ -297,14 +353,14 @@ __device__ __forceinline__ void exit_step(const SceneView& sv, const TallySink& 
     const V3 nw = map_vector(rec + kNodeL2W, nl);
     double c = fabs(dot(nw, ph.d));
     if (c > 1.0) c = 1.0;
-    tally(sv, T, ph, PVT_REC_EXIT, hit, true, nw, lp, c);
+    tr.sel = PVT_REC_EXIT; tr.node = hit; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c;
   }
 }
 
 // Absorbed in the volume (:762-832).  Returns true while the photon lives (re-emitted or scattered).
 template <class Rng, class P>
-__device__ __forceinline__ bool volume_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
-                                            const StepParams& sp, P& ph, Rng& rng, LaneStats& st, const StepPlan& plan) {
+__device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
+                                            Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const Header& H = sv.hdr();
   const int container = plan.container;
   advance(ph, plan.t, sv.node(container)[kNodeIndex]);
@@ -320,7 +376,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const TallySink
     if (target <= running) { comp = c0 + k; break; }
   }
   ++st.events;
-  PVT_LOG(ph, PVT_EV_ABSORB, -1, container, -1, comp, nullptr);
+  PVT_LOG(ph, PVT_EV_ABSORB, -1, container, -1, comp);
   const double* cr = sv.comp(comp);
   const int ctype = sv.comp_int(comp, CI_TYPE);
   bool radiative = false;
@@ -353,39 +409,39 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const TallySink
         if (!Rng::kAddressed) u_delay = rng.one(kBlockEmit, 1);
         ph.duration += -log(1.0 - u_delay) * cr[kCompTauRad];
       }
-      PVT_LOG(ph, PVT_EV_EMIT, -1, container, -1, comp, nullptr);
+      PVT_LOG(ph, PVT_EV_EMIT, -1, container, -1, comp);
     } else {
-      PVT_LOG(ph, PVT_EV_SCATTER, -1, container, -1, comp, nullptr);
+      PVT_LOG(ph, PVT_EV_SCATTER, -1, container, -1, comp);
     }
     return true;
   }
-  if (cr[kCompTauNr] > 0.0) ph.duration += -log(1.0 - rng.one(kBlockEmit, 1)) * cr[kCompTauNr];
+  if (cr[kCompTauNr] > 0.0) ph.duration += -log(1.0 - rng.one_rare(kBlockEmit, 1)) * cr[kCompTauNr];
   ++st.events;
   int sel;
   if (ctype == PVT_COMP_REACTOR) {
-    PVT_LOG(ph, PVT_EV_REACT, -1, container, -1, comp, nullptr);
+    PVT_LOG(ph, PVT_EV_REACT, -1, container, -1, comp);
     sel = PVT_REC_REACTED;
   } else {
-    PVT_LOG(ph, PVT_EV_NONRADIATIVE, -1, container, -1, comp, nullptr);
+    PVT_LOG(ph, PVT_EV_NONRADIATIVE, -1, container, -1, comp);
     sel = PVT_REC_LOST;
   }
   if (H.n_recorders > 0) {
     const V3 lp = map_point(sv.node(container) + kNodeW2L, ph.p);
-    tally(sv, T, ph, sel, container, false, V3{0.0, 0.0, 0.0}, lp, 1.0);
+    tr.sel = sel; tr.node = container; tr.has_normal = false; tr.normal = V3{0.0, 0.0, 0.0}; tr.lp = lp; tr.cosine = 1.0;
   }
   return false;
 }
 
 // Reaches a surface that is not the root boundary (:834-895).  Returns true while the photon lives.
 template <class Rng, class P>
-__device__ __forceinline__ bool surface_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
-                                             const StepParams& sp, P& ph, Rng& rng, LaneStats& st, const StepPlan& plan) {
+__device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
+                                             Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit, container = plan.container, adjacent = plan.adjacent;
   const double n1 = sv.node(container)[kNodeIndex];
   advance(ph, plan.t, n1);
   ++st.events;
   if (adjacent < 0) {
-    PVT_LOG(ph, PVT_EV_KILL, hit, container, -1, -1, nullptr);
+    PVT_LOG(ph, PVT_EV_KILL, hit, container, -1, -1);
     return false;
   }
   const double* hrec = sv.node(hit);
@@ -418,26 +474,26 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const TallySin
   if (u < R) {
     if (lambert) {
       double p1, p2;
-      rng.pair(kBlockLambert, p1, p2);
+      rng.pair_rare(kBlockLambert, p1, p2);
       ph.d = lambert_about(neg(nf), p1, p2);
     } else {
       ph.d = mirror(ph.d, nw);
     }
-    PVT_LOG(ph, PVT_EV_REFLECT, hit, container, adjacent, -1, &nw);
+    PVT_LOG_N(ph, PVT_EV_REFLECT, hit, container, adjacent, -1, true, nw);
     sel = PVT_REC_REFLECTED;
     record = record && container != hit;
   } else {
     if (fresnel && !straight) ph.d = snell(ph.d, nf, n1, n2);
-    PVT_LOG(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, &nw);
+    PVT_LOG_N(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, true, nw);
     sel = container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING;
   }
-  if (record) tally(sv, T, ph, sel, hit, true, nw, lp, c);
+  if (record) { tr.sel = sel; tr.node = hit; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c; }
   return true;
 }
 
 // ---- on-device emission of the built-in light delegates (emit.py:22-134; scene.py:141-151) ---------------
 // Uniform k of Philox stream kStreamEmit of ray id: k=0 wavelength, k=1..3 position, k=4,5 direction.
-__device__ __forceinline__ void emit_ray(const SceneView& sv, u64 id, long long index, V3& pos, V3& dir, double& wl) {
+__device__ __noinline__ void emit_ray(const SceneView sv, u64 id, long long index, V3& pos, V3& dir, double& wl) {
   const Header& H = sv.hdr();
   const int l = (int)(index % H.n_lights);
   const double* q = sv.light(l);

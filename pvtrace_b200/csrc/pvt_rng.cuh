@@ -83,6 +83,10 @@ struct PhiloxStream {
     u1 = u53(r.z, r.w);
   }
   __device__ __forceinline__ double next() { return philox_uniform_at(id, kStreamTrace, k++); }
+  // out-of-line copies for draws that almost never happen (delays, Lambertian mirrors): keeps the ten rounds
+  // out of the hot instruction stream
+  __device__ __noinline__ double one_rare(uint32_t b, uint32_t half) { return one(b, half); }
+  __device__ __noinline__ void pair_rare(uint32_t b, double& u0, double& u1) { pair(b, u0, u1); }
 };
 
 // The reference's generator: draws are consumed in program order, addresses are ignored.
@@ -109,6 +113,8 @@ struct XoshiroStream {
   }
   __device__ __forceinline__ double one(uint32_t, uint32_t) { return next(); }
   __device__ __forceinline__ void pair(uint32_t, double& u0, double& u1) { u0 = next(); u1 = next(); }
+  __device__ __forceinline__ double one_rare(uint32_t, uint32_t) { return next(); }
+  __device__ __forceinline__ void pair_rare(uint32_t, double& u0, double& u1) { u0 = next(); u1 = next(); }
 };
 
 }  // namespace pvt
