@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the photon-tracing hot path: photons/s on the 5x5x1 cm LSC (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--photons P] [--config NAME] [--impl reference]
+
+One "step" = one pass of the hot path over one bundle of P photons (default 10^7, BASELINE.json configs[1]:
+LSC((5,5,1)) default Lumogen-F-Red scene, emit_method kT, maxsteps 1000, record: true-style recorders, no event
+log).  Under torchrun every rank traces its own P photons (weak scaling, disjoint photon-index ranges of one
+global run) and the step ends with ONE all-reduce of the packed tally buffer.
+
+Printed JSON (rank 0):
+  value      photons/s with the initial rays ALREADY RESIDENT in HBM (device time, CUDA events, max over ranks)
+  e2e        photons/s through the reference-facing call `_cuda.trace_bundle` == pvt_trace_bundle (C ABI) with
+             HOST (pinned) ray arrays: H2D of positions/directions/wavelengths + trace + D2H of the tallies inside
+             the timed region
+  roofline   dominant kernel vs the HBM roofline: achieved = photon steps (device counter) x 192 B / kernel time,
+             peak = MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own compiled kernel (oracle/_ref, built from /root/reference) on the host cores
+`--impl reference` times that CPU kernel alone, same metric, same config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGORITHMIC_BYTES_PER_STEP = 192  # 96 B photon state read + written once per photon step
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--photons", type=float, default=1e7, help="photons per GPU per step")
+    ap.add_argument("--config", default="lsc_default")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-sample", type=float, default=2e6, help="photons per CPU-baseline repetition")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def build_scene(name):
+    import pvtrace_b200 as pv
+    from pvtrace_b200.device import configs
+    from pvtrace_b200.engine.compiler import EMIT_METHODS
+
+    build, kw = configs.CONFIGS[name]
+    scene = build()
+    return scene, pv.engine.compile_scene(scene), pv.engine.compile_emitter(scene), EMIT_METHODS[kw["emit_method"]]
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([f.strip() for f in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def time_reference_kernel(compiled, emitter, method, photons, reps, threads):
+    """photons/s of the reference's compiled CPU kernel (oracle/_ref) on `threads` host threads, best of reps."""
+    from oracle import pvt_oracle, ref_loader
+
+    kernel = ref_loader.load_ref_kernel()
+    kind = "reference"
+    n = int(photons)
+    pos, direction, wl = pvt_oracle.emit_bundle(emitter, n, seed=1)
+    best = None
+    for _ in range(reps):
+        tic = time.perf_counter()
+        if kernel is not None:
+            kernel.trace_bundle(compiled, pos, direction, wl, 1, 1000, 128, method, threads, 0)
+        else:  # reference tree was not available at build time: the oracle port stands in
+            kind = "port"
+            pvt_oracle.trace_bundle(compiled, pos, direction, wl, 1, 1000, 128, method, threads, 0, rng_mode=1)
+        dt = time.perf_counter() - tic
+        best = dt if best is None else min(best, dt)
+    return n / best, kind, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, compiled, emitter, method = build_scene(args.config)
+    threads = os.cpu_count() or 1
+    sample = int(min(args.photons, args.cpu_sample))
+    for _ in range(max(args.warmup, 0)):
+        time_reference_kernel(compiled, emitter, method, min(sample, 200000), 1, threads)
+    times = []
+    for _ in range(args.steps):
+        rate, kind, dt = time_reference_kernel(compiled, emitter, method, sample, 1, threads)
+        times.append(dt)
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": "photons/sec on 5x5x1 cm LSC", "value": value, "unit": "photons/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: LSC((5,5,1)) Lumogen F Red 305, kT emission, maxsteps 1000, "
+                               f"record_every 0; step = {sample} photons (bounded sample of the 1e7-photon bundle)",
+                   "photons_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "photons/s", "cores": threads, "kind": kind,
+                         "sample": f"{sample} photons per step, pvtrace/engine/_kernel.pyx compiled -O3 -fopenmp, "
+                                   f"{threads} OpenMP threads"},
+        "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from pvtrace_b200.engine import _cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (pvtrace_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    scene, compiled, emitter, method = build_scene(args.config)
+    n = int(args.photons)
+    seed = 1
+    first_index = rank * n  # disjoint photon-index ranges of one global run of world * n photons
+    ctx = _cuda.Context(compiled, emitter, local)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    # ---- device-resident leg: initial rays live in HBM before the timed region ---------------------------
+    pos = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    dirs = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    wl = torch.empty(n, dtype=torch.float64, device="cuda")
+    ctx.emit(pos.data_ptr(), dirs.data_ptr(), wl.data_ptr(), n, seed=seed, first_index=first_index, stream=sptr)
+
+    class _Packed:  # zero-copy torch view of the library's packed tally buffer (for the NCCL all-reduce)
+        def __init__(self, ptr, count):
+            self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def one_step():
+        ctx.reset(stream=sptr)
+        ctx.trace(n, seed, d_positions=pos.data_ptr(), d_directions=dirs.data_ptr(), d_wavelengths=wl.data_ptr(),
+                  first_index=first_index, emit_method=method, record_every=0, stream=sptr)
+        if world > 1:
+            ptr, count = ctx.pack_tallies(stream=sptr)
+            packed = torch.as_tensor(_Packed(ptr, count), device="cuda")
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            ctx.unpack_tallies(stream=sptr)
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    fence()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    kernel_events = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for _ in range(args.steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.reset(stream=sptr)
+        a.record(stream)
+        ctx.trace(n, seed, d_positions=pos.data_ptr(), d_directions=dirs.data_ptr(), d_wavelengths=wl.data_ptr(),
+                  first_index=first_index, emit_method=method, record_every=0, stream=sptr)
+        b.record(stream)
+        kernel_events.append((a, b))
+        if world > 1:
+            ptr, count = ctx.pack_tallies(stream=sptr)
+            packed = torch.as_tensor(_Packed(ptr, count), device="cuda")
+            dist.all_reduce(packed, op=dist.ReduceOp.SUM)
+            ctx.unpack_tallies(stream=sptr)
+    stop.record(stream)
+    fence()
+    clocks = sampler.stop() if sampler else None
+    total_ms = start.elapsed_time(stop)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    data = ctx.read(stream=sptr)
+    steps_per_bundle = int(data["stats"][_cuda.STAT_STEPS])  # accumulated since the last reset == one bundle
+    launches_per_step = 1 + (2 if world > 1 else 0)
+
+    # ---- end-to-end leg: host (pinned) rays through the drop-in call -----------------------------------------
+    h_pos = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    h_dir = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+    h_wl = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_pos.copy_(pos); h_dir.copy_(dirs); h_wl.copy_(wl)
+    torch.cuda.synchronize()
+    np_pos, np_dir, np_wl = h_pos.numpy(), h_dir.numpy(), h_wl.numpy()
+
+    def e2e_step():
+        out, elapsed = _cuda.trace_bundle(compiled, np_pos, np_dir, np_wl, seed, 1000, 128, method, 0, 0,
+                                          first_index=first_index, device=local, return_elapsed=True)
+        if world > 1:
+            from pvtrace_b200.engine import distributed
+
+            out = distributed.all_reduce_tallies(out)
+        return out, elapsed
+
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        e2e_step()
+    fence()
+    tic = time.perf_counter()
+    for _ in range(e2e_steps):
+        out, _ = e2e_step()
+    fence()
+    e2e_s = (time.perf_counter() - tic) / e2e_steps
+    h2d = int(np_pos.nbytes + np_dir.nbytes + np_wl.nbytes)
+    d2h = int(sum(out[k].nbytes for k in ("rec_distinct", "rec_crossings", "rec_sums", "rec_bins", "stats")))
+
+    # ---- reduce timings over ranks (max) ---------------------------------------------------------------------
+    times = torch.tensor([total_ms, kernel_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms, e2e_s = (float(v) for v in times.tolist())
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ms_per_step = total_ms / args.steps
+        value = world * n / (ms_per_step * 1e-3)
+        achieved = steps_per_bundle * ALGORITHMIC_BYTES_PER_STEP / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(prof):
+            with open(prof) as fh:
+                traffic = json.load(fh).get(args.config)
+        line = {
+            "metric": "photons/sec on 5x5x1 cm LSC", "value": value, "unit": "photons/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: LSC((5,5,1)) Lumogen F Red 305 x10 cm^-1 + 0.1 cm^-1 background, "
+                                   "555 nm cone(20 deg) light, kT emission, maxsteps 1000, record:true recorders "
+                                   "(7808 bins), record_every 0",
+                       "photons_per_gpu_per_step": n, "photon_steps_per_gpu_per_step": steps_per_bundle,
+                       "l2": "initial rays 56 B/photon (560 MB at 1e7) exceed the 126 MB L2",
+                       "sharding": f"photon index ranges, {world} rank(s), one all-reduce of the packed tallies per step"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "wavefront_kernel",
+                         "kernel_ms": kernel_ms, "bytes_per_step": ALGORITHMIC_BYTES_PER_STEP},
+            "e2e": {"value": world * n / e2e_s, "unit": "photons/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            rate, kind, dt = time_reference_kernel(compiled, emitter, method, min(args.cpu_sample, n), 3, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": "photons/s", "cores": threads, "kind": kind,
+                                    "sample": f"{int(min(args.cpu_sample, n))} photons of the same scene, best of 3, "
+                                              f"{threads} OpenMP threads, pvtrace/engine/_kernel.pyx -O3 -fopenmp"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -206,6 +206,9 @@ typedef struct pvt_out_t {
 int         pvt_version(void);
 int         pvt_device_count(void);      /* 0 when no CUDA device/driver is usable */
 const char* pvt_last_error(void);
+/* sizeof(pvt_scene_t), sizeof(pvt_emit_t), sizeof(pvt_params_t), sizeof(pvt_out_t): lets a foreign-function
+ * binding verify its struct mirrors against the compiled library */
+void        pvt_struct_sizes(int32_t sizes[4]);
 
 /* ---------------------------------------------------------------- drop-in trace (host buffers) -------- *
  * Replaces _kernel.trace_bundle (_kernel.pyx:903-1115).  `positions`/`directions` are [n,3], `wavelengths`

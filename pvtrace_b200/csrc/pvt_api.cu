@@ -572,6 +572,10 @@ extern "C" int pvt_device_count(void) {
   return n;
 }
 extern "C" const char* pvt_last_error(void) { return error_buffer(); }
+extern "C" void pvt_struct_sizes(int32_t sizes[4]) {
+  sizes[0] = (int32_t)sizeof(pvt_scene_t); sizes[1] = (int32_t)sizeof(pvt_emit_t);
+  sizes[2] = (int32_t)sizeof(pvt_params_t); sizes[3] = (int32_t)sizeof(pvt_out_t);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Known-answer helpers: upload, one launch, download.

@@ -202,6 +202,7 @@ def load_library():
         "pvt_version": (C.c_int, []),
         "pvt_device_count": (C.c_int, []),
         "pvt_last_error": (C.c_char_p, []),
+        "pvt_struct_sizes": (None, [C.POINTER(C.c_int32)]),
         "pvt_trace_bundle": (C.c_int, [C.POINTER(PvtScene), C.POINTER(PvtEmit), vp, vp, vp,
                                        C.POINTER(PvtParams), C.POINTER(PvtOut), _P_F64]),
         "pvt_context_create": (C.c_int, [C.POINTER(PvtScene), C.POINTER(PvtEmit), C.c_int, C.POINTER(vp)]),
@@ -227,12 +228,17 @@ def load_library():
     for name, (restype, argtypes) in protos.items():
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
         fn.restype, fn.argtypes = restype, argtypes
+    sizes = (C.c_int32 * 4)()
+    lib.pvt_struct_sizes(sizes)
+    mine = [C.sizeof(PvtScene), C.sizeof(PvtEmit), C.sizeof(PvtParams), C.sizeof(PvtOut)]
+    if list(sizes) != mine:
+        raise LibraryError(f"struct layout mismatch between {LIB_PATH} {list(sizes)} and its ctypes mirror {mine}")
     _lib = lib
     return lib
 
 
 EXPORTED_SYMBOLS = (
-    "pvt_version", "pvt_device_count", "pvt_last_error", "pvt_trace_bundle", "pvt_context_create",
+    "pvt_version", "pvt_device_count", "pvt_last_error", "pvt_struct_sizes", "pvt_trace_bundle", "pvt_context_create",
     "pvt_context_destroy", "pvt_context_reset", "pvt_trace_device", "pvt_context_read",
     "pvt_context_pack_tallies", "pvt_context_unpack_tallies", "pvt_emit_device", "pvt_emit_bundle",
     "pvt_intersect_bundle", "pvt_intersect_device", "pvt_test_fresnel_reflectivity",
