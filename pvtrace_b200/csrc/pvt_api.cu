@@ -110,8 +110,8 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
 }
 
 struct WaveVariant { int threads, ctas; };
-constexpr int kWaveVariants = 8;
-static const WaveVariant kWaveTable[kWaveVariants] = {{1024, 1}, {768, 1}, {512, 2}, {512, 1}, {384, 2}, {256, 4}, {256, 3}, {256, 2}};
+constexpr int kWaveVariants = 6;
+static const WaveVariant kWaveTable[kWaveVariants] = {{1024, 1}, {768, 1}, {640, 1}, {512, 2}, {512, 1}, {384, 2}};
 
 template <class K>
 static int wave_attr(K kernel, size_t smem) {
@@ -122,13 +122,17 @@ static int wave_attr(K kernel, size_t smem) {
 // launches (or, with args == nullptr, only configures) the wavefront variant chosen for the context
 #define PVT_WAVE_CASE(T, B)                                                                      \
   if (c->wave_threads == T && c->wave_ctas == B) {                                               \
-    if (!args) return wave_attr(wavefront_kernel<T, B>, c->wave_smem);                           \
-    wavefront_kernel<T, B><<<grid, T, c->wave_smem, st>>>(*args);                                \
+    if (!args) {                                                                                 \
+      PVT_TRY(wave_attr(wavefront_kernel<T, B, false>, c->wave_smem));                           \
+      return wave_attr(wavefront_kernel<T, B, true>, c->wave_smem);                              \
+    }                                                                                            \
+    if (args->record_every > 0) wavefront_kernel<T, B, true><<<grid, T, c->wave_smem, st>>>(*args);  \
+    else wavefront_kernel<T, B, false><<<grid, T, c->wave_smem, st>>>(*args);                    \
     return 0;                                                                                    \
   }
 static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
-  PVT_WAVE_CASE(1024, 1) PVT_WAVE_CASE(768, 1) PVT_WAVE_CASE(512, 2) PVT_WAVE_CASE(512, 1)
-  PVT_WAVE_CASE(384, 2) PVT_WAVE_CASE(256, 4) PVT_WAVE_CASE(256, 3) PVT_WAVE_CASE(256, 2)
+  PVT_WAVE_CASE(1024, 1) PVT_WAVE_CASE(768, 1) PVT_WAVE_CASE(640, 1) PVT_WAVE_CASE(512, 2) PVT_WAVE_CASE(512, 1)
+  PVT_WAVE_CASE(384, 2)
   return fail("no wavefront kernel variant for %d threads x %d CTAs", c->wave_threads, c->wave_ctas);
 }
 
@@ -159,7 +163,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   // wavefront kernel: needs the blob AND the photon pool in shared memory, <= 64 recorders (seen mask), <= 254 nodes
   c->wave_threads = 0;
   if (c->R() <= 64) {
-    int want_t = 512, want_b = 2;
+    int want_t = 640, want_b = 1;
     if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) want_t = atoi(env);
     if (const char* env = getenv("PVT_WAVEFRONT_CTAS")) want_b = atoi(env);
     for (int k = 0; k < kWaveVariants && want_t > 0; ++k) {

@@ -126,16 +126,21 @@ __device__ __noinline__ int sampled_ordinal(long long i, long long record_every)
 // =========================================================================================================
 // wavefront_kernel
 
-// Shared-memory pool of P photon slots, structure of arrays.  kPoolDoubles double columns, then 64-bit, 32-bit
-// and 16-bit columns; column c of slot s is at base + c * P + s.
+// Shared-memory pool of P photon slots, structure of arrays: 12 f64 columns, the seen mask, six 32-bit columns,
+// three u16 queues; then the ring of prefetched initial rays (7 f64 columns of K entries) and the counters.
 constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
 constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, idx, ids, log_ray (< 0: not sampled)
+__host__ __device__ constexpr int ring_size(int P) { return P >= 512 ? 512 : 256; }
 __host__ __device__ constexpr size_t pool_bytes(int P) {
-  return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + 64 /*counters*/;
+  return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + (size_t)ring_size(P) * 7 * 8 +
+         64 /*counters*/;
 }
 __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
   return 16 + (size_t)blob_words * 8 + pool_bytes(P);
 }
+
+// counters (u32): [0..3], [4..7] queue lengths, double buffered by iteration parity; then the cursors of the slice
+enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrCount = 16 };
 
 struct PoolView {
   double *px, *py, *pz, *dx, *dy, *dz, *wl, *trav, *dur, *t, *u, *alpha;
@@ -143,7 +148,8 @@ struct PoolView {
   int32_t *count, *source, *nlog, *log_ray;
   uint32_t *idx, *ids;
   uint16_t *qv, *qs, *qe;
-  uint32_t* counters;  // [2][4] queue lengths, double buffered by iteration parity; [8..9] next index of the slice
+  double* ring;        // [7][K]: px py pz dx dy dz wl of photons [ring_lo, ring_hi) of the slice, at offset mod K
+  uint32_t* counters;
 };
 
 __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
@@ -152,7 +158,8 @@ __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
   v.px = d; v.py = d + P; v.pz = d + 2 * P; v.dx = d + 3 * P; v.dy = d + 4 * P; v.dz = d + 5 * P;
   v.wl = d + 6 * P; v.trav = d + 7 * P; v.dur = d + 8 * P; v.t = d + 9 * P; v.u = d + 10 * P; v.alpha = d + 11 * P;
   v.seen = reinterpret_cast<u64*>(d + 12 * P);
-  int32_t* w = reinterpret_cast<int32_t*>(d + 13 * P);
+  v.ring = d + 13 * P;
+  int32_t* w = reinterpret_cast<int32_t*>(v.ring + 7 * ring_size(P));
   v.count = w; v.source = w + P; v.nlog = w + 2 * P;
   v.idx = reinterpret_cast<uint32_t*>(w + 3 * P); v.ids = reinterpret_cast<uint32_t*>(w + 4 * P);
   v.log_ray = w + 5 * P;
@@ -164,22 +171,35 @@ __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
 
 typedef PhotonT<2> PoolPhoton;
 
-__device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, int max_events) {
+// what classify needs of a slot
+template <bool kLog>
+__device__ __forceinline__ void load_slot_head(const PoolView& pool, int s, PoolPhoton& ph, int max_events) {
   ph.p = V3{pool.px[s], pool.py[s], pool.pz[s]};
   ph.d = V3{pool.dx[s], pool.dy[s], pool.dz[s]};
-  ph.wl = pool.wl[s]; ph.travelled = pool.trav[s]; ph.duration = pool.dur[s];
-  ph.count = pool.count[s]; ph.source = pool.source[s]; ph.nlog = pool.nlog[s];
+  ph.wl = pool.wl[s];
+  ph.count = pool.count[s];
+  ph.log_ray = -1; ph.log_base = -1; ph.nlog = 0;
+  if (kLog) {
+    ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; ph.source = pool.source[s];
+    ph.nlog = pool.nlog[s];
+    ph.log_ray = pool.log_ray[s];
+    ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * max_events;
+  }
+}
+template <bool kLog>
+__device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, int max_events) {
+  load_slot_head<kLog>(pool, s, ph, max_events);
+  ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; ph.source = pool.source[s];
   const u64 seen = pool.seen[s];
   ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
-  ph.log_ray = pool.log_ray[s];
-  ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * max_events;
 }
+template <bool kLog>
 __device__ __forceinline__ void store_slot(const PoolView& pool, int s, const PoolPhoton& ph) {
   pool.px[s] = ph.p.x; pool.py[s] = ph.p.y; pool.pz[s] = ph.p.z;
   pool.dx[s] = ph.d.x; pool.dy[s] = ph.d.y; pool.dz[s] = ph.d.z;
   pool.wl[s] = ph.wl; pool.trav[s] = ph.travelled; pool.dur[s] = ph.duration;
-  pool.source[s] = ph.source; pool.nlog[s] = ph.nlog;
-  pool.seen[s] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);
+  pool.source[s] = ph.source;
+  if (kLog) pool.nlog[s] = ph.nlog;
 }
 
 // append slot `s` to queue `q` for the lanes where `pred` holds: one shared atomic per warp
@@ -193,9 +213,23 @@ __device__ __forceinline__ void push_queue(uint16_t* q, uint32_t* counter, bool 
   if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)s;
 }
 
-template <int T, int B>
+// initial state of photon i of the bundle (global arrays or the emitter); out of line: the common path takes
+// fresh rays from the shared-memory ring that the spare warps keep filled
+__device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, long long i, V3& p, V3& d, double& wl) {
+  if (a.pos) {
+    p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
+    d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
+    wl = a.wl[i];
+  } else {
+    emit_ray(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i, p, d, wl);
+  }
+}
+
+template <int T, int B, bool kLog>
 __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
-  constexpr int P = T - 64;  // two warps have no home slot: room for the warp padding of the queues in stage 2
+  constexpr int P = T - 64;  // two warps own no slot: they produce fresh rays in stage 1 and absorb the warp
+                             // padding of the queues in stage 2
+  constexpr int K = ring_size(P);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
@@ -204,7 +238,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
   const PoolView pool = carve_pool(smem_raw + 16 + (size_t)a.blob_words * 8, P);
   const int R = sv.hdr().n_recorders;
   const TallySink sink = cta_sink(a, R);
-  const PhiloxStream rng0{a.seed + (u64)a.first_index, 0u, 0u};
+  const u64 id0 = a.seed + (u64)a.first_index;
   const StepParams sp = a.sp;
   const LogColumns& L = a.log;
 
@@ -213,14 +247,15 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
   const long long slice_lo = a.n * (long long)blockIdx.x / gridDim.x;
   const long long slice_hi = a.n * (long long)(blockIdx.x + 1) / gridDim.x;
   const uint32_t slice_n = (uint32_t)(slice_hi - slice_lo);
-  if (tid < 12) pool.counters[tid] = 0u;
+  if (tid < kCtrCount) pool.counters[tid] = 0u;
   if (tid < P) pool.count[tid] = -1;
   __syncthreads();
 
   LaneStats st;
   for (uint32_t iter = 0;; ++iter) {
     uint32_t* qn = pool.counters + 4 * (iter & 1);
-    // ---------------- stage 1: refill + classify, slot == tid -----------------------------------------
+    const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
+    // ---------------- stage 1: refill + classify (slot == tid); the spare warps produce rays ---------------
     bool live = false;
     if (tid < P) {
       PoolPhoton ph;
@@ -230,49 +265,72 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
       if (m) {
         uint32_t base = 0;
         const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(pool.counters + 8, (uint32_t)__popc(m));
+        if (lane == leader) base = atomicAdd(pool.counters + kCtrNext, (uint32_t)__popc(m));
         base = __shfl_sync(kFullMask, base, leader);
         const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
         if (dead && mine < slice_n) {
           const long long i = slice_lo + mine;
-          const u64 id = rng0.id + (u64)i;
-          if (a.pos) {
-            ph.p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
-            ph.d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
-            ph.wl = a.wl[i];
+          if (mine < ring_hi) {
+            const double* r = pool.ring + (mine & (K - 1));
+            ph.p = V3{r[0], r[K], r[2 * K]};
+            ph.d = V3{r[3 * K], r[4 * K], r[5 * K]};
+            ph.wl = r[6 * K];
           } else {
-            emit_ray(sv, id, a.first_index + i, ph.p, ph.d, ph.wl);
+            fetch_ray(a, sv, i, ph.p, ph.d, ph.wl);
           }
-          ph.log_ray = a.record_every > 0 ? sampled_ordinal(i, a.record_every) : -1;
+          ph.log_ray = (kLog && a.record_every > 0) ? sampled_ordinal(i, a.record_every) : -1;
           ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
-          begin_photon(ph, L, sp, st);
+          begin_photon<kLog>(ph, L, sp, st);
           pool.idx[tid] = mine;
-          pool.log_ray[tid] = ph.log_ray;
+          if (kLog) pool.log_ray[tid] = ph.log_ray;
+          pool.seen[tid] = 0ull;
           fresh = true;
         }
       }
       StepClass cls = kDead;
       if (fresh || !dead) {
-        if (!fresh) load_slot(pool, tid, ph, sp.max_events);
-        PhiloxStream rng = rng0;
-        rng.id += (u64)(slice_lo + pool.idx[tid]);
+        if (!fresh) load_slot_head<kLog>(pool, tid, ph, sp.max_events);
+        PhiloxStream rng;
+        rng.id = id0 + (u64)(slice_lo + pool.idx[tid]);
         StepPlan plan;
-        cls = classify_step(sv, sink, L, sp, ph, rng, st, plan);
+        cls = classify_step<kLog>(sv, L, sp, ph, rng, st, plan);
         if (cls == kDead) {
-          if (ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
+          if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
           pool.count[tid] = -1;
         } else {
-          if (fresh) store_slot(pool, tid, ph);
+          if (fresh) store_slot<kLog>(pool, tid, ph);
           pool.count[tid] = ph.count;
           pool.t[tid] = plan.t; pool.u[tid] = plan.u; pool.alpha[tid] = plan.alpha;
           pool.ids[tid] = (uint32_t)(plan.hit & 0xff) | ((uint32_t)(plan.container & 0xff) << 8) |
-                          ((uint32_t)(plan.adjacent & 0xff) << 16);
+                          ((uint32_t)(plan.adjacent & 0xff) << 16) | (cls == kKill ? 1u << 24 : 0u);
           live = true;
         }
       }
       push_queue(pool.qv, qn + 0, cls == kVolume, tid, lane);
       push_queue(pool.qs, qn + 1, cls == kSurface, tid, lane);
-      push_queue(pool.qe, qn + 2, cls == kExit, tid, lane);
+      push_queue(pool.qe, qn + 2, cls == kExit || cls == kKill, tid, lane);
+    } else {
+      // producer warps: rays [max(ring_hi, next), next + K) of the slice into the ring.  `next` is the snapshot
+      // taken at the last barrier, so the entries the consumers read in this stage are never overwritten.
+      const uint32_t next = pool.counters[kCtrNextSnap];
+      uint32_t lo = ring_hi > next ? ring_hi : next;
+      uint32_t hi = next + (uint32_t)K;
+      if (hi > slice_n) hi = slice_n;
+      for (uint32_t o = lo + (uint32_t)(tid - P); o < hi; o += (uint32_t)(T - P)) {
+        V3 p, d;
+        double w;
+        const long long i = slice_lo + o;
+        if (a.pos) {
+          p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
+          d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
+          w = a.wl[i];
+        } else {
+          emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
+        }
+        double* r = pool.ring + (o & (K - 1));
+        r[0] = p.x; r[K] = p.y; r[2 * K] = p.z; r[3 * K] = d.x; r[4 * K] = d.y; r[5 * K] = d.z; r[6 * K] = w;
+      }
+      if (tid == P) pool.counters[kCtrRingHiPending] = hi > lo ? hi : lo;
     }
     if (!__syncthreads_or(live)) break;
 
@@ -280,30 +338,35 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
     const int cv = (int)qn[0], cs = (int)qn[1], ce = (int)qn[2];
     const int pv = (cv + 31) & ~31, ps = (cs + 31) & ~31;
     if (tid < 4) pool.counters[4 * ((iter + 1) & 1) + tid] = 0u;
+    if (tid == T - 1) {  // publish the cursors for the next iteration (nobody refills or produces in stage 2)
+      pool.counters[kCtrRingHi] = pool.counters[kCtrRingHiPending];
+      pool.counters[kCtrNextSnap] = pool.counters[kCtrNext];
+    }
     int slot = -1, cls = kDead;
     if (tid < pv) { if (tid < cv) { slot = pool.qv[tid]; cls = kVolume; } }
     else if (tid < pv + ps) { if (tid - pv < cs) { slot = pool.qs[tid - pv]; cls = kSurface; } }
     else if (tid - pv - ps < ce) { slot = pool.qe[tid - pv - ps]; cls = kExit; }
     if (slot >= 0) {
       PoolPhoton ph;
-      load_slot(pool, slot, ph, sp.max_events);
-      PhiloxStream rng = rng0;
-      rng.id += (u64)(slice_lo + pool.idx[slot]);
+      load_slot<kLog>(pool, slot, ph, sp.max_events);
+      PhiloxStream rng;
+      rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
       rng.begin_step((uint32_t)ph.count);
       StepPlan plan;
       plan.t = pool.t[slot]; plan.u = pool.u[slot]; plan.alpha = pool.alpha[slot];
       const uint32_t ids = pool.ids[slot];
       plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
       if (plan.adjacent == 0xff) plan.adjacent = -1;
-      bool alive;
+      bool alive = false;
       TallyReq tr;
-      if (cls == kVolume) alive = volume_step(sv, L, sp, ph, rng, st, plan, tr);
-      else if (cls == kSurface) alive = surface_step(sv, L, sp, ph, rng, st, plan, tr);
-      else { exit_step(sv, L, sp, ph, st, plan, tr); alive = false; }
+      if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+      else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+      else if (ids >> 24) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
+      else exit_step<kLog>(sv, L, sp, ph, st, plan, tr);
       if (alive) {
-        store_slot(pool, slot, ph);
+        store_slot<kLog>(pool, slot, ph);
       } else {
-        if (ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
+        if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
         pool.count[slot] = -1;
       }
       if (tr.sel >= 0) {
@@ -378,7 +441,7 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
           rng.init(id);
           ph.log_ray = a.record_every > 0 ? sampled_ordinal(idx, a.record_every) : -1;
           ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
-          begin_photon(ph, L, sp, st);
+          begin_photon<true>(ph, L, sp, st);
           alive = true;
         } else {
           exhausted = true;  // the global counter is past n: nothing will ever arrive
@@ -388,12 +451,13 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a)
     if (!__any_sync(kFullMask, alive)) break;
     if (alive) {
       StepPlan plan;
-      const StepClass cls = classify_step(sv, sink, L, sp, ph, rng, st, plan);
+      const StepClass cls = classify_step<true>(sv, L, sp, ph, rng, st, plan);
       TallyReq tr;
-      if (cls == kVolume) alive = volume_step(sv, L, sp, ph, rng, st, plan, tr);
-      else if (cls == kSurface) alive = surface_step(sv, L, sp, ph, rng, st, plan, tr);
+      if (cls == kVolume) alive = volume_step<true>(sv, L, sp, ph, rng, st, plan, tr);
+      else if (cls == kSurface) alive = surface_step<true>(sv, L, sp, ph, rng, st, plan, tr);
       else {
-        if (cls == kExit) exit_step(sv, L, sp, ph, st, plan, tr);
+        if (cls == kExit) exit_step<true>(sv, L, sp, ph, st, plan, tr);
+        else if (cls == kKill) kill_step<true>(sv, L, sp, ph, st, plan, tr);
         alive = false;
       }
       if (tr.sel >= 0) tally(sv, sink, ph, tr);

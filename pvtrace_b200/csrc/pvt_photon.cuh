@@ -53,7 +53,7 @@ struct PhotonT {
   uint32_t seen[kSeenWords];
 };
 
-enum StepClass { kDead = 0, kExit = 1, kVolume = 2, kSurface = 3 };
+enum StepClass { kDead = 0, kExit = 1, kVolume = 2, kSurface = 3, kKill = 4 };  // kKill: step budget exhausted
 
 struct Nearest {
   double t0;
@@ -122,10 +122,11 @@ __device__ __noinline__ void log_event(const LogColumns& L, long long row, int k
   if (has_normal) { L.normal[3 * row] = normal.x; L.normal[3 * row + 1] = normal.y; L.normal[3 * row + 2] = normal.z; }
   L.wavelength[row] = wl; L.travelled[row] = travelled; L.duration[row] = duration;
 }
-// log one event of photon `ph` if the ray is sampled and has budget left
+// log one event of photon `ph` if the ray is sampled and has budget left; `kLog` is a compile-time flag of the
+// enclosing function: kernels instantiated for record_every == 0 carry no logging code at all
 #define PVT_LOG_N(ph, kind, hit, cont, adj, comp, has_n, nrm)                                                          \
   do {                                                                                                                 \
-    if ((ph).log_base >= 0 && (ph).nlog < sp.max_events) {                                                             \
+    if (kLog && (ph).log_base >= 0 && (ph).nlog < sp.max_events) {                                                     \
       log_event(L, (ph).log_base + (ph).nlog, kind, hit, cont, adj, comp, (ph).source, (ph).p, (ph).d, has_n, nrm,     \
                 (ph).wl, (ph).travelled, (ph).duration);                                                               \
       ++(ph).nlog;                                                                                                     \
@@ -160,33 +161,35 @@ struct SeenMask {
   uint32_t w[SW];
 };
 
-// One copy of the recorder loop for the whole kernel (every stage calls it warp-convergently).  `cosine` is the
-// cosine of the incidence angle (1 for volume events => angle 0); acos is taken only when a recorder matches for
-// the first time.  Returns the updated distinct-ray mask.
+// `cosine` is the cosine of the incidence angle (1 for volume events => angle 0); acos is taken only when a
+// recorder matches for the first time.  The candidates are the recorders attached to (node, selector) -- usually
+// none to six -- looked up in the blob's index; lanes search independently and update together.
 template <int SW>
-__device__ __noinline__ SeenMask<SW> tally_event(const SceneView sv, const TallySink T, SeenMask<SW> seen, int sel,
-                                                 int node, bool has_normal, V3 wnormal, V3 lp, double cosine, double wl,
-                                                 double duration, double travelled) {
-  const int R = sv.hdr().n_recorders;
+__device__ __forceinline__ SeenMask<SW> tally_event(const SceneView& sv, const TallySink& T, SeenMask<SW> seen, int sel,
+                                                    int node, bool has_normal, const V3& wnormal, const V3& lp,
+                                                    double cosine, double wl, double duration, double travelled) {
+  int k, k_end;
+  sv.rec_range(node, sel, k, k_end);
+  k_end += k;
   double angle = -1.0;
-  int r = -1;
   for (;;) {
-    // next recorder matching (node, selector[, facet]); lanes search independently, then update together
-    for (++r; r < R; ++r) {
-      if (sv.rec_int(r, RI_NODE) != node || sv.rec_int(r, RI_EVENT) != sel) continue;
-      if (!sv.rec_int(r, RI_HAS_FACET)) break;
+    int r = -1;
+    for (; k < k_end; ++k) {
+      const int cand = sv.rec_candidate(k);
+      if (!sv.rec_int(cand, RI_HAS_FACET)) { r = cand; break; }
       if (!has_normal) continue;
-      const double* q = sv.rec(r);
+      const double* q = sv.rec(cand);
       const double tol = q[kRecAtol];
-      if (fabs(q[0] - wnormal.x) <= tol && fabs(q[1] - wnormal.y) <= tol && fabs(q[2] - wnormal.z) <= tol) break;
+      if (fabs(q[0] - wnormal.x) <= tol && fabs(q[1] - wnormal.y) <= tol && fabs(q[2] - wnormal.z) <= tol) { r = cand; break; }
     }
-    if (r >= R) break;
+    if (r < 0) break;
+    ++k;
     red_add(&T.cross[r], 1ull);
     const uint32_t bit = 1u << (r & 31);
     bool was_seen = false;
 #pragma unroll
-    for (int k = 0; k < SW; ++k)
-      if (k == (r >> 5)) { was_seen = (seen.w[k] & bit) != 0; seen.w[k] |= bit; }
+    for (int w = 0; w < SW; ++w)
+      if (w == (r >> 5)) { was_seen = (seen.w[w] & bit) != 0; seen.w[w] |= bit; }
     if (was_seen) continue;
     if (angle < 0.0) angle = cosine >= 1.0 ? 0.0 : acos(cosine);
     red_add(&T.distinct[r], 1ull);
@@ -215,20 +218,8 @@ __device__ __noinline__ SeenMask<SW> tally_event(const SceneView sv, const Tally
   return seen;
 }
 
-template <class P>
-__device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, int sel, int node,
-                                      bool has_normal, const V3& wnormal, const V3& lp, double cosine) {
-  constexpr int SW = (int)(sizeof(ph.seen) / 4);
-  SeenMask<SW> seen;
-#pragma unroll
-  for (int k = 0; k < SW; ++k) seen.w[k] = ph.seen[k];
-  seen = tally_event<SW>(sv, T, seen, sel, node, has_normal, wnormal, lp, cosine, ph.wl, ph.duration, ph.travelled);
-#pragma unroll
-  for (int k = 0; k < SW; ++k) ph.seen[k] = seen.w[k];
-}
-
-// A stage does not tally itself: it fills in a request and the kernel makes the (single, out-of-line) call once
-// the photon has been written back, when almost nothing is live in registers.
+// A stage does not tally itself: it fills in a request and the kernel makes the single (inlined) call once the
+// photon has been written back, when almost nothing is live in registers.
 struct TallyReq {
   int sel = -1;  // PVT_REC_*, < 0: nothing to tally
   int node;
@@ -239,7 +230,14 @@ struct TallyReq {
 
 template <class P>
 __device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P& ph, const TallyReq& tr) {
-  tally(sv, T, ph, tr.sel, tr.node, tr.has_normal, tr.normal, tr.lp, tr.cosine);
+  constexpr int SW = (int)(sizeof(ph.seen) / 4);
+  SeenMask<SW> seen;
+#pragma unroll
+  for (int k = 0; k < SW; ++k) seen.w[k] = ph.seen[k];
+  seen = tally_event<SW>(sv, T, seen, tr.sel, tr.node, tr.has_normal, tr.normal, tr.lp, tr.cosine, ph.wl, ph.duration,
+                         ph.travelled);
+#pragma unroll
+  for (int k = 0; k < SW; ++k) ph.seen[k] = seen.w[k];
 }
 
 // facet-surface extension: first facet of `node` whose LOCAL normal equals nl within its tolerance
@@ -266,7 +264,7 @@ struct LaneStats {
   uint32_t steps = 0, events = 0, rays = 0;
 };
 
-template <class P>
+template <bool kLog, class P>
 __device__ __forceinline__ void begin_photon(P& ph, const LogColumns& L, const StepParams& sp, LaneStats& st) {
   ph.travelled = 0.0; ph.duration = 0.0;
   ph.source = -1; ph.count = 0; ph.nlog = 0;
@@ -285,15 +283,16 @@ struct StepPlan {
 };
 
 // First half of the reference's loop body (_kernel.pyx:654-760): budget check, intersect, kill check, free path.
-template <class Rng, class P>
-__device__ __forceinline__ StepClass classify_step(const SceneView& sv, const TallySink& T, const LogColumns& L,
-                                                   const StepParams& sp, P& ph, Rng& rng, LaneStats& st, StepPlan& plan) {
+// Touches nothing but position, direction, wavelength and the step counter.
+template <bool kLog, class Rng, class P>
+__device__ __forceinline__ StepClass classify_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
+                                                   Rng& rng, LaneStats& st, StepPlan& plan) {
   const Header& H = sv.hdr();
   plan.u = 1.0; plan.alpha = 0.0;
   ++ph.count;
   rng.begin_step((uint32_t)ph.count);
   // event budget of sampled rays: keep room for the KILL record (:658-663)
-  if (ph.log_base >= 0 && ph.nlog >= sp.max_events - 1) {
+  if (kLog && ph.log_base >= 0 && ph.nlog >= sp.max_events - 1) {
     ++st.events;
     PVT_LOG(ph, PVT_EV_KILL, -1, -1, -1, -1);
     return kDead;
@@ -303,16 +302,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Ta
   if (nh.total == 0) return kDead;  // :681-682
   plan.hit = nh.hit; plan.container = nh.container; plan.adjacent = nh.adjacent;
   plan.t = nh.t0;
-
-  if (ph.count > sp.maxsteps) {  // :716-723
-    ++st.events;
-    PVT_LOG(ph, PVT_EV_KILL, -1, nh.container, -1, -1);
-    if (H.n_recorders > 0) {
-      const V3 lp = map_point(sv.node(nh.container) + kNodeW2L, ph.p);
-      tally(sv, T, ph, PVT_REC_KILLED, nh.container, false, V3{0.0, 0.0, 0.0}, lp, 1.0);
-    }
-    return kDead;
-  }
+  if (ph.count > sp.maxsteps) return kKill;  // :716-723, completed by kill_step
   if (nh.hit == H.root_id) return kExit;
 
   // Beer-Lambert free path in the container (material.py:17-47 == :746-760)
@@ -338,8 +328,20 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Ta
   return kSurface;
 }
 
+// Step budget exhausted (:716-723): KILL record and `killed` tally on the container, no movement.
+template <bool kLog, class P>
+__device__ __forceinline__ void kill_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
+                                          LaneStats& st, const StepPlan& plan, TallyReq& tr) {
+  ++st.events;
+  PVT_LOG(ph, PVT_EV_KILL, -1, plan.container, -1, -1);
+  if (sv.hdr().n_recorders > 0) {
+    tr.sel = PVT_REC_KILLED; tr.node = plan.container; tr.has_normal = false; tr.normal = V3{0.0, 0.0, 0.0};
+    tr.lp = map_point(sv.node(plan.container) + kNodeW2L, ph.p); tr.cosine = 1.0;
+  }
+}
+
 // Leaves the scene through the root boundary (:728-744).
-template <class P>
+template <bool kLog, class P>
 __device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
                                           LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit;
@@ -358,7 +360,7 @@ __device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns&
 }
 
 // Absorbed in the volume (:762-832).  Returns true while the photon lives (re-emitted or scattered).
-template <class Rng, class P>
+template <bool kLog, class Rng, class P>
 __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
                                             Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const Header& H = sv.hdr();
@@ -433,7 +435,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
 }
 
 // Reaches a surface that is not the root boundary (:834-895).  Returns true while the photon lives.
-template <class Rng, class P>
+template <bool kLog, class Rng, class P>
 __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
                                              Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit, container = plan.container, adjacent = plan.adjacent;

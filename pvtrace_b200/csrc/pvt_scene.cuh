@@ -15,6 +15,9 @@
 //   hists       n_hists      x kHistWords
 //   facets      n_facets     x kFacetWords
 //   lights      n_lights     x kLightWords, wl_x, wl_cdf
+//   rec_index   n_nodes x kRecSelectors (start, count) int pairs into rec_list: the recorders attached to
+//               (node, selector), so a tally looks at its handful of candidates instead of every recorder
+//   rec_list    n_recorders int32 recorder indices grouped by (node, selector), original order within a group
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -27,7 +30,7 @@ namespace pvt {
 struct Header {
   int32_t n_nodes, root_id, n_components, n_recorders, n_hists, total_bins, n_facets, n_lights;
   int32_t off_nodes, off_comps, off_abs_x, off_abs_y, off_ems_x, off_ems_cdf, off_recs, off_hists;
-  int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, pad0, pad1, pad2;
+  int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, off_rec_index, off_rec_list, pad2;
 };
 constexpr int kHeaderWords = sizeof(Header) / 8;
 static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
@@ -45,6 +48,7 @@ constexpr int kHistLoA = 0, kHistHiA = 1, kHistLoB = 2, kHistHiB = 3, kHistInts 
 // facet record: normal xyz, atol, reflectivity | ints: flags,pad | pad pad
 constexpr int kFacetNormal = 0, kFacetAtol = 3, kFacetRefl = 4, kFacetInts = 5, kFacetWords = 8;
 // light record: l2w rows 0-2 (12) | pos_param (3) | dir_param | wl_param | ints: pos_kind,dir_kind | wl_kind,wl_start | wl_n,pad
+constexpr int kRecSelectors = 8;  // PVT_REC_* selectors 0..6, padded to 8
 constexpr int kLightL2W = 0, kLightPos = 12, kLightDir = 15, kLightWl = 16, kLightInts = 17, kLightWords = 20;
 
 // 1/dx when xs[0..n) is an (almost) uniform ascending grid: every knot within 0.45 dx of xs[0] + i dx, so a
@@ -85,6 +89,8 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
   h.off_lights = w;  w += h.n_lights * kLightWords;
   h.off_wl_x = w;    w += E ? E->n_wl_knots : 0;
   h.off_wl_cdf = w;  w += E ? E->n_wl_knots : 0;
+  h.off_rec_index = w; w += S.n_nodes * kRecSelectors;
+  h.off_rec_list = w;  w += (S.n_recorders + 1) / 2;
   w = (w + 1) & ~1;
   h.total_words = w;
 
@@ -153,6 +159,17 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
     put_ints(blob, iw + 1, E->wl_kind[l], E->wl_start[l]);
     put_ints(blob, iw + 2, E->wl_n[l], 0);
   }
+  {
+    int32_t* list = reinterpret_cast<int32_t*>(&blob[h.off_rec_list]);
+    int32_t filled = 0;
+    for (int node = 0; node < S.n_nodes; ++node)
+      for (int sel = 0; sel < kRecSelectors; ++sel) {
+        const int32_t start = filled;
+        for (int r = 0; r < S.n_recorders; ++r)
+          if (S.rec_node[r] == node && S.rec_event[r] == sel) list[filled++] = r;
+        put_ints(blob, h.off_rec_index + (size_t)node * kRecSelectors + sel, start, filled - start);
+      }
+  }
   if (E && E->n_wl_knots) {
     memcpy(&blob[h.off_wl_x], E->wl_x, E->n_wl_knots * sizeof(double));
     memcpy(&blob[h.off_wl_cdf], E->wl_cdf, E->n_wl_knots * sizeof(double));
@@ -176,6 +193,12 @@ struct SceneView {
   __device__ __forceinline__ int hist_int(int h, int k) const { return ival(hdr().off_hists + h * kHistWords + kHistInts + (k >> 1), k & 1); }
   __device__ __forceinline__ const double* facet(int f) const { return w + hdr().off_facets + f * kFacetWords; }
   __device__ __forceinline__ int facet_flags(int f) const { return ival(hdr().off_facets + f * kFacetWords + kFacetInts, 0); }
+  // recorders attached to (node, selector): rec_candidate(start + k), k < count
+  __device__ __forceinline__ void rec_range(int node, int sel, int& start, int& count) const {
+    const int word = hdr().off_rec_index + node * kRecSelectors + sel;
+    start = ival(word, 0); count = ival(word, 1);
+  }
+  __device__ __forceinline__ int rec_candidate(int k) const { return reinterpret_cast<const int32_t*>(w + hdr().off_rec_list)[k]; }
   __device__ __forceinline__ const double* light(int l) const { return w + hdr().off_lights + l * kLightWords; }
   __device__ __forceinline__ int light_int(int l, int k) const { return ival(hdr().off_lights + l * kLightWords + kLightInts + (k >> 1), k & 1); }
 };
