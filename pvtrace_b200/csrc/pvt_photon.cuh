@@ -67,12 +67,27 @@ __device__ __forceinline__ Nearest nearest_surface(const SceneView& sv, const V3
   const int n_nodes = sv.hdr().n_nodes;
   double t_first = PVT_INF, t_second = PVT_INF, t_single = PVT_INF;
   int n_first = -1, n_second = -1, n_single = -1, total = 0;
+  V3 inv_world;           // 1 / d, shared by every axis-aligned box (their local direction IS d)
+  bool have_inv = false;
   for (int node = 0; node < n_nodes; ++node) {
     const double* rec = sv.node(node);
-    const V3 o = map_point(rec + kNodeW2L, p);
-    const V3 dl = map_vector(rec + kNodeW2L, d);
+    const int gtype = sv.node_int(node, NI_GEOM);
     double ts[4];
-    const int k = roots(sv.node_int(node, NI_GEOM), rec + kNodeParams, o, dl, ts);
+    int k;
+    if (sv.node_int(node, NI_ALIGNED)) {
+      // rotation part of w2l is the identity: o = p + translation exactly as the full product would give
+      const V3 o = V3{p.x + rec[kNodeW2L + 3], p.y + rec[kNodeW2L + 7], p.z + rec[kNodeW2L + 11]};
+      if (gtype == 0) {
+        if (!have_inv) { inv_world = slab_reciprocal(d); have_inv = true; }
+        k = roots_box(rec[kNodeParams], rec[kNodeParams + 1], rec[kNodeParams + 2], o, d, inv_world, ts);
+      } else {
+        k = roots(gtype, rec + kNodeParams, o, d, ts);
+      }
+    } else {
+      const V3 o = map_point(rec + kNodeW2L, p);
+      const V3 dl = map_vector(rec + kNodeW2L, d);
+      k = roots(gtype, rec + kNodeParams, o, dl, ts);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < k) {
@@ -252,11 +267,12 @@ __device__ __forceinline__ int find_facet(const SceneView& sv, int node, const V
   return -1;
 }
 
+// `slowness` = n / c of the container (seconds per cm), precomputed per node
 template <class P>
-__device__ __forceinline__ void advance(P& ph, double t, double n_container) {
+__device__ __forceinline__ void advance(P& ph, double t, double slowness) {
   ph.p = axpy(ph.p, ph.d, t);
   ph.travelled += t;
-  ph.duration += t * n_container / kLightSpeed;
+  ph.duration += t * slowness;
 }
 
 // Per-lane run statistics (device counters of pvt_out_t.stats)
@@ -345,7 +361,7 @@ template <bool kLog, class P>
 __device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
                                           LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit;
-  advance(ph, plan.t, sv.node(plan.container)[kNodeIndex]);
+  advance(ph, plan.t, sv.node(plan.container)[kNodeSlowness]);
   ++st.events;
   PVT_LOG(ph, PVT_EV_EXIT, hit, plan.container, plan.adjacent, -1);
   if (sv.hdr().n_recorders > 0) {
@@ -365,7 +381,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
                                             Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const Header& H = sv.hdr();
   const int container = plan.container;
-  advance(ph, plan.t, sv.node(container)[kNodeIndex]);
+  advance(ph, plan.t, sv.node(container)[kNodeSlowness]);
   const int c0 = sv.node_int(container, NI_COMP_START), cn = sv.node_int(container, NI_COMP_COUNT);
   double u_target, u_yield;
   if (Rng::kAddressed) rng.pair(kBlockAbsorb, u_target, u_yield);
@@ -440,7 +456,7 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
                                              Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit, container = plan.container, adjacent = plan.adjacent;
   const double n1 = sv.node(container)[kNodeIndex];
-  advance(ph, plan.t, n1);
+  advance(ph, plan.t, sv.node(container)[kNodeSlowness]);
   ++st.events;
   if (adjacent < 0) {
     PVT_LOG(ph, PVT_EV_KILL, hit, container, -1, -1);

@@ -35,8 +35,10 @@ struct Header {
 constexpr int kHeaderWords = sizeof(Header) / 8;
 static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
 
-// node record: w2l rows 0-2 (12) | l2w rows 0-2 (12) | params (4) | n (1) | ints: geom,surf | comp_start,comp_count | facet_start,facet_count
-constexpr int kNodeW2L = 0, kNodeL2W = 12, kNodeParams = 24, kNodeIndex = 28, kNodeInts = 29, kNodeWords = 32;
+// node record: w2l rows 0-2 (12) | l2w rows 0-2 (12) | params (4) | n (1) | ints: geom,surf | comp_start,comp_count |
+// facet_start,facet_count | n / c (seconds per cm) | ints: aligned (rotation part of w2l is exactly the identity), pad
+constexpr int kNodeW2L = 0, kNodeL2W = 12, kNodeParams = 24, kNodeIndex = 28, kNodeInts = 29, kNodeSlowness = 32,
+              kNodeWords = 34;
 // component record: qy, tau_rad, tau_nr, phase_param | ints: type,phase_type | abs_start,abs_n | ems_start,ems_n |
 // abs_inv_dx, ems_inv_dx (1/spacing of the x grid when it is uniform enough for interp_hinted, else 0) | pad
 constexpr int kCompQy = 0, kCompTauRad = 1, kCompTauNr = 2, kCompPhaseParam = 3, kCompInts = 4, kCompAbsInvDx = 7,
@@ -51,15 +53,15 @@ constexpr int kFacetNormal = 0, kFacetAtol = 3, kFacetRefl = 4, kFacetInts = 5, 
 constexpr int kRecSelectors = 8;  // PVT_REC_* selectors 0..6, padded to 8
 constexpr int kLightL2W = 0, kLightPos = 12, kLightDir = 15, kLightWl = 16, kLightInts = 17, kLightWords = 20;
 
-// 1/dx when xs[0..n) is an (almost) uniform ascending grid: every knot within 0.45 dx of xs[0] + i dx, so a
-// guessed bracket is at most one knot away from the true one.  0 otherwise.
+// 1/dx when xs[0..n) is a uniform ascending grid (every knot within 1e-9 dx of xs[0] + i dx, so multiplying by
+// 1/dx stands in for dividing by the local spacing, and a guessed bracket is at most one knot off).  0 otherwise.
 inline double uniform_inv_dx(const double* xs, int n) {
   if (n < 3) return 0.0;
   const double dx = (xs[n - 1] - xs[0]) / (n - 1);
   if (!(dx > 0.0)) return 0.0;
   for (int i = 0; i < n; ++i) {
     const double dev = xs[i] - (xs[0] + i * dx);
-    if (dev > 0.45 * dx || dev < -0.45 * dx) return 0.0;
+    if (dev > 1e-9 * dx || dev < -1e-9 * dx) return 0.0;
   }
   return 1.0 / dx;
 }
@@ -106,6 +108,11 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
     put_ints(blob, iw, S.geom_type[i], S.surface_type[i]);
     put_ints(blob, iw + 1, S.comp_start[i], S.comp_count[i]);
     put_ints(blob, iw + 2, h.n_facets ? S.facet_start[i] : 0, h.n_facets ? S.facet_count[i] : 0);
+    r[kNodeSlowness] = S.refractive_index[i] / 2.99792458e10;
+    const double* m = S.world_to_local + 16 * i;
+    const bool aligned = m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[4] == 0.0 && m[5] == 1.0 && m[6] == 0.0 &&
+                         m[8] == 0.0 && m[9] == 0.0 && m[10] == 1.0;
+    put_ints(blob, iw + 4, aligned ? 1 : 0, 0);
   }
   for (int c = 0; c < S.n_components; ++c) {
     double* r = &blob[h.off_comps + (size_t)c * kCompWords];
@@ -203,7 +210,8 @@ struct SceneView {
   __device__ __forceinline__ int light_int(int l, int k) const { return ival(hdr().off_lights + l * kLightWords + kLightInts + (k >> 1), k & 1); }
 };
 // int slots of the records
-enum { NI_GEOM = 0, NI_SURF = 1, NI_COMP_START = 2, NI_COMP_COUNT = 3, NI_FACET_START = 4, NI_FACET_COUNT = 5 };
+enum { NI_GEOM = 0, NI_SURF = 1, NI_COMP_START = 2, NI_COMP_COUNT = 3, NI_FACET_START = 4, NI_FACET_COUNT = 5,
+       NI_ALIGNED = 8 };
 enum { CI_TYPE = 0, CI_PHASE = 1, CI_ABS_START = 2, CI_ABS_N = 3, CI_EMS_START = 4, CI_EMS_N = 5 };
 enum { RI_NODE = 0, RI_EVENT = 1, RI_HAS_FACET = 2, RI_HIST_START = 3, RI_HIST_N = 4 };
 enum { HI_PROP_A = 0, HI_PROP_B = 1, HI_NA = 2, HI_NB = 3, HI_OFFSET = 4 };

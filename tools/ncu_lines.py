@@ -49,3 +49,37 @@ def text(k):
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     st = ",".join(f"{n}:{v}" for n, v in a[3].most_common(3))
     print(f"{100 * a[0] / tot[0]:5.1f}% samp  {100 * a[1] / tot[1]:5.1f}% inst  lanes {a[2] / max(a[1], 1):5.1f}  {str(k):32s} {st:45s} {text(k)}")
+
+# ---- per function: thread-instructions (the work) and warp-instructions (the issue slots) -----------------
+import bisect
+funcs = {}
+for fname, lines in src.items():
+    starts = []
+    for no, text_ in enumerate(lines, 1):
+        m = re.match(r'\s*(?:template <[^>]*>\s*)?(?:__device__|__global__|__host__).*?\b(\w+)\s*\(', text_)
+        if m and not text_.strip().startswith("//"):
+            starts.append((no, m.group(1)))
+    funcs[fname] = starts
+def func_of(k):
+    if not k: return "?"
+    st = funcs.get(k[0])
+    if st is None:
+        p = os.path.join(root, "pvtrace_b200/csrc", k[0])
+        if os.path.exists(p):
+            src[k[0]] = open(p).read().splitlines()
+            starts = []
+            for no, text_ in enumerate(src[k[0]], 1):
+                m = re.match(r'\s*(?:template <[^>]*>\s*)?(?:__device__|__global__|__host__).*?\b(\w+)\s*\(', text_)
+                if m and not text_.strip().startswith("//"): starts.append((no, m.group(1)))
+            funcs[k[0]] = st = starts
+        else:
+            return k[0]
+    i = bisect.bisect_right([s[0] for s in st], k[1]) - 1
+    return f"{k[0]}:{st[i][1]}" if i >= 0 else k[0]
+by = collections.defaultdict(lambda: [0, 0, 0])
+for k, a in agg.items():
+    f = func_of(k)
+    by[f][0] += a[0]; by[f][1] += a[1]; by[f][2] += a[2]
+print("\nper function:  samples%  warp-inst%  thread-inst%  lanes")
+for f, a in sorted(by.items(), key=lambda kv: -kv[1][1])[:30]:
+    print(f"{100 * a[0] / tot[0]:6.1f} {100 * a[1] / tot[1]:6.1f} {100 * a[2] / tot[2]:6.1f} {a[2] / max(a[1], 1):6.1f}  {f}")
