@@ -85,7 +85,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.02)
 
     def stop(self):
         self._halt.set()
@@ -229,6 +229,35 @@ def run_b200(args):
     steps_per_bundle = int(data["stats"][_cuda.STAT_STEPS])  # accumulated since the last reset == one bundle
     launches_per_step = 1 + (2 if world > 1 else 0)
 
+    # ---- the intersect stage on its own (north_star: "HBM roofline for the intersect kernel") ----------------
+    t0 = torch.empty(n, dtype=torch.float64, device="cuda")
+    ids = torch.empty((3, n), dtype=torch.int32, device="cuda")
+    for _ in range(3):
+        ctx.intersect(pos.data_ptr(), dirs.data_ptr(), n, t0.data_ptr(), ids[0].data_ptr(), ids[1].data_ptr(),
+                      ids[2].data_ptr(), stream=sptr)
+    ia, ib = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ia.record(stream)
+    for _ in range(5):
+        ctx.intersect(pos.data_ptr(), dirs.data_ptr(), n, t0.data_ptr(), ids[0].data_ptr(), ids[1].data_ptr(),
+                      ids[2].data_ptr(), stream=sptr)
+    ib.record(stream)
+    torch.cuda.synchronize()
+    intersect_ms = ia.elapsed_time(ib) / 5
+    del t0, ids
+
+    # ---- the user-facing call with on-device emission (no ray arrays cross PCIe) --------------------------------
+    def emit_step():
+        return _cuda.trace_bundle(compiled, None, None, None, seed, 1000, 128, method, 0, 0, emitter=emitter, n=n,
+                                  first_index=first_index, device=local, return_elapsed=True)
+
+    emit_step()
+    fence()
+    tic = time.perf_counter()
+    for _ in range(3):
+        emit_step()
+    fence()
+    emit_s = (time.perf_counter() - tic) / 3
+
     # ---- end-to-end leg: host (pinned) rays through the drop-in call -----------------------------------------
     h_pos = torch.empty((n, 3), dtype=torch.float64).pin_memory()
     h_dir = torch.empty((n, 3), dtype=torch.float64).pin_memory()
@@ -289,6 +318,12 @@ def run_b200(args):
                          "kernel_ms": kernel_ms, "bytes_per_step": ALGORITHMIC_BYTES_PER_STEP},
             "e2e": {"value": world * n / e2e_s, "unit": "photons/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
+            "e2e_device_emission": {"value": world * n / emit_s, "unit": "photons/s", "ms_per_step": 1e3 * emit_s,
+                                    "note": "engine.simulate path for built-in lights: rays sampled in the kernel, "
+                                            "0 B H2D, tallies D2H"},
+            "intersect_stage": {"kernel": "intersect_kernel", "ms": intersect_ms, "bytes_per_ray": 68,
+                                "achieved_gbs": 68.0 * n / (intersect_ms * 1e-3) / 1e9,
+                                "frac_of_hbm_peak": 68.0 * n / (intersect_ms * 1e-3) / 1e9 / peak},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }

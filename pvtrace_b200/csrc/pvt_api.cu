@@ -448,6 +448,9 @@ struct Timer {
   }
 };
 
+constexpr int kMaxChunks = 8;            // pieces a host bundle is uploaded + traced in
+constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each
+
 // One cached context per process: bundles of the same scene (engine.simulate_stream, repeated simulate calls)
 // reuse the uploaded blob and every device buffer.
 std::mutex g_cache_mutex;
@@ -481,23 +484,62 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   pvt_context* c = nullptr;
   PVT_TRY(acquire_context(scene, emit, params->device, &c));
   PVT_CUDA(cudaSetDevice(c->device));
-  Timer timer;
-  PVT_TRY(timer.start());
-  const size_t n = (size_t)params->n;
-  const double *d_pos = nullptr, *d_dir = nullptr, *d_wl = nullptr;
-  if (have_rays && n > 0) {
-    if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
-    PVT_TRY(g_rays.reserve(7 * n));
-    PVT_CUDA(cudaMemcpyAsync(g_rays.ptr, positions, 24 * n, cudaMemcpyHostToDevice, 0));
-    PVT_CUDA(cudaMemcpyAsync(g_rays.ptr + 3 * n, directions, 24 * n, cudaMemcpyHostToDevice, 0));
-    PVT_CUDA(cudaMemcpyAsync(g_rays.ptr + 6 * n, wavelengths, 8 * n, cudaMemcpyHostToDevice, 0));
-    d_pos = g_rays.ptr; d_dir = g_rays.ptr + 3 * n; d_wl = g_rays.ptr + 6 * n;
+  // two non-blocking streams: host rays are uploaded in chunks on one while the previous chunk is traced on the
+  // other (overlap needs page-locked host memory; with pageable memory the copies simply serialise)
+  static cudaStream_t s_copy = nullptr, s_run = nullptr;
+  static cudaEvent_t s_uploaded[kMaxChunks] = {nullptr};
+  static int s_device = -1;
+  if (s_device != c->device) {
+    if (s_copy) { cudaStreamDestroy(s_copy); cudaStreamDestroy(s_run); for (auto& e : s_uploaded) cudaEventDestroy(e); }
+    PVT_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    PVT_CUDA(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+    for (auto& e : s_uploaded) PVT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s_device = c->device;
   }
-  PVT_TRY(pvt_context_reset(c, 0));
-  PVT_TRY(pvt_trace_device(c, d_pos, d_dir, d_wl, params, 0));
-  PVT_TRY(pvt_context_read(c, out, 0));
-  PVT_TRY(timer.stop(elapsed_s));
-  return 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  PVT_CUDA(cudaEventCreate(&t0));
+  PVT_CUDA(cudaEventCreate(&t1));
+  PVT_CUDA(cudaEventRecord(t0, s_run));
+  int rc = pvt_context_reset(c, s_run);
+  const size_t n = (size_t)params->n;
+  if (!rc && have_rays && n > 0) {
+    if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
+    rc = g_rays.reserve(7 * n);
+    double *d_pos = g_rays.ptr, *d_dir = g_rays.ptr + 3 * n, *d_wl = g_rays.ptr + 6 * n;
+    // the event log is indexed by the ray's position in the bundle, so logged bundles go in one piece
+    int chunks = (params->record_every == 0 && n >= (size_t)kMinChunkRays * 2) ? (int)(n / kMinChunkRays) : 1;
+    if (chunks > kMaxChunks) chunks = kMaxChunks;
+    for (int k = 0; k < chunks && !rc; ++k) {
+      const size_t lo = n * k / chunks, hi = n * (k + 1) / chunks, m = hi - lo;
+      cudaError_t e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir + 3 * lo, directions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_wl + lo, wavelengths + lo, 8 * m, cudaMemcpyHostToDevice, s_copy);
+      if (e == cudaSuccess) e = cudaEventRecord(s_uploaded[k], s_copy);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, s_uploaded[k], 0);
+      if (e != cudaSuccess) { rc = fail("ray upload failed: %s", cudaGetErrorString(e)); break; }
+      pvt_params_t part = *params;
+      part.n = (int64_t)m;
+      part.first_index = params->first_index + (int64_t)lo;
+      rc = pvt_trace_device(c, d_pos + 3 * lo, d_dir + 3 * lo, d_wl + lo, &part, s_run);
+    }
+  } else if (!rc) {
+    rc = pvt_trace_device(c, nullptr, nullptr, nullptr, params, s_run);
+  }
+  if (!rc) rc = pvt_context_read(c, out, s_run);
+  if (!rc) {
+    cudaError_t e = cudaEventRecord(t1, s_run);
+    if (e == cudaSuccess) e = cudaEventSynchronize(t1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, t0, t1);
+    if (e != cudaSuccess) rc = fail("timing failed: %s", cudaGetErrorString(e));
+    else if (elapsed_s) *elapsed_s = ms * 1e-3;
+  } else {
+    cudaStreamSynchronize(s_run);
+    cudaStreamSynchronize(s_copy);
+  }
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return rc;
 }
 
 extern "C" int pvt_emit_bundle(const pvt_emit_t* emit, double* positions, double* directions, double* wavelengths, int64_t n,
