@@ -50,6 +50,7 @@ struct pvt_context {
   DeviceBuffer<u64> slabs;  // CTA-private tally slabs of one launch: [max_grid][10 R]
   int max_grid = 0;
   int wave_threads = 0;     // CTA size of the wavefront kernel for this scene, 0: scene needs trace_kernel
+  int wave_pool = 0;        // photon slots per CTA
   int wave_ctas = 1;        // resident CTAs per SM
   size_t wave_smem = 0;
   // event log of the last trace
@@ -109,9 +110,13 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
   return 0;
 }
 
-struct WaveVariant { int threads, ctas; };
-constexpr int kWaveVariants = 6;
-static const WaveVariant kWaveTable[kWaveVariants] = {{1024, 1}, {768, 1}, {640, 1}, {512, 2}, {512, 1}, {384, 2}};
+// (threads, pool slots, resident CTAs per SM), preferred first; the first that fits the scene's shared memory wins
+struct WaveVariant { int threads, pool, ctas; };
+constexpr int kWaveVariants = 14;
+static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {640, 1152, 1}, {1024, 1024, 1}, {768, 1024, 1},
+                                                      {512, 768, 1},  {640, 640, 1},  {512, 512, 1},   {512, 512, 2},
+                                                      {384, 768, 1},  {256, 512, 1},  {512, 1280, 1},  {640, 1280, 1},
+                                                      {576, 1152, 1}, {448, 1344, 1}};
 
 template <class K>
 static int wave_attr(K kernel, size_t smem) {
@@ -120,20 +125,22 @@ static int wave_attr(K kernel, size_t smem) {
 }
 
 // launches (or, with args == nullptr, only configures) the wavefront variant chosen for the context
-#define PVT_WAVE_CASE(T, B)                                                                      \
-  if (c->wave_threads == T && c->wave_ctas == B) {                                               \
+#define PVT_WAVE_CASE(T, P, B)                                                                   \
+  if (c->wave_threads == T && c->wave_pool == P && c->wave_ctas == B) {                          \
     if (!args) {                                                                                 \
-      PVT_TRY(wave_attr(wavefront_kernel<T, B, false>, c->wave_smem));                           \
-      return wave_attr(wavefront_kernel<T, B, true>, c->wave_smem);                              \
+      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false>, c->wave_smem));                        \
+      return wave_attr(wavefront_kernel<T, P, B, true>, c->wave_smem);                           \
     }                                                                                            \
-    if (args->record_every > 0) wavefront_kernel<T, B, true><<<grid, T, c->wave_smem, st>>>(*args);  \
-    else wavefront_kernel<T, B, false><<<grid, T, c->wave_smem, st>>>(*args);                    \
+    if (args->record_every > 0) wavefront_kernel<T, P, B, true><<<grid, T, c->wave_smem, st>>>(*args);  \
+    else wavefront_kernel<T, P, B, false><<<grid, T, c->wave_smem, st>>>(*args);                 \
     return 0;                                                                                    \
   }
 static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
-  PVT_WAVE_CASE(1024, 1) PVT_WAVE_CASE(768, 1) PVT_WAVE_CASE(640, 1) PVT_WAVE_CASE(512, 2) PVT_WAVE_CASE(512, 1)
-  PVT_WAVE_CASE(384, 2)
-  return fail("no wavefront kernel variant for %d threads x %d CTAs", c->wave_threads, c->wave_ctas);
+  PVT_WAVE_CASE(1024, 1024, 1) PVT_WAVE_CASE(768, 1024, 1) PVT_WAVE_CASE(640, 1152, 1) PVT_WAVE_CASE(640, 640, 1)
+  PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(512, 768, 1) PVT_WAVE_CASE(512, 512, 1) PVT_WAVE_CASE(512, 512, 2)
+  PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1) PVT_WAVE_CASE(512, 1280, 1) PVT_WAVE_CASE(640, 1280, 1)
+  PVT_WAVE_CASE(576, 1152, 1) PVT_WAVE_CASE(448, 1344, 1)
+  return fail("no wavefront kernel variant for %d threads / %d slots x %d CTAs", c->wave_threads, c->wave_pool, c->wave_ctas);
 }
 
 extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context_t** out) {
@@ -163,15 +170,16 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   // wavefront kernel: needs the blob AND the photon pool in shared memory, <= 64 recorders (seen mask), <= 254 nodes
   c->wave_threads = 0;
   if (c->R() <= 64) {
-    int want_t = 640, want_b = 1;
+    int want_t = 0, want_p = 0, want_b = 0;  // 0: any
     if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) want_t = atoi(env);
+    if (const char* env = getenv("PVT_WAVEFRONT_POOL")) want_p = atoi(env);
     if (const char* env = getenv("PVT_WAVEFRONT_CTAS")) want_b = atoi(env);
-    for (int k = 0; k < kWaveVariants && want_t > 0; ++k) {
-      const int t = kWaveTable[k].threads, b = kWaveTable[k].ctas;
-      if (t > want_t || (t == want_t && b > want_b)) continue;  // table is ordered: largest first
-      const size_t need = wavefront_smem_bytes(c->blob_words, t - 64);
+    for (int k = 0; k < kWaveVariants && want_t >= 0; ++k) {
+      const int t = kWaveTable[k].threads, pl = kWaveTable[k].pool, b = kWaveTable[k].ctas;
+      if ((want_t && t != want_t) || (want_p && pl != want_p) || (want_b && b != want_b)) continue;
+      const size_t need = wavefront_smem_bytes(c->blob_words, pl);
       if ((need + 1024) * b <= (size_t)prop.sharedMemPerMultiprocessor && need <= (size_t)prop.sharedMemPerBlockOptin) {
-        c->wave_threads = t; c->wave_ctas = b; c->wave_smem = need;
+        c->wave_threads = t; c->wave_pool = pl; c->wave_ctas = b; c->wave_smem = need;
         break;
       }
     }
@@ -299,7 +307,7 @@ extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const dou
   int grid;
   if (c->wave_threads > 0 && P->rng_mode == PVT_RNG_PHILOX && !megakernel_forced) {
     // one persistent CTA per SM, each owning a contiguous slice of the photon range
-    const int pool = c->wave_threads - 64;
+    const int pool = c->wave_pool;
     const long long want_blocks = (P->n + pool - 1) / pool;
     const long long resident = (long long)c->sm_count * c->wave_ctas;
     grid = (int)(want_blocks < resident ? want_blocks : resident);

@@ -130,7 +130,7 @@ __device__ __noinline__ int sampled_ordinal(long long i, long long record_every)
 // three u16 queues; then the ring of prefetched initial rays (7 f64 columns of K entries) and the counters.
 constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
 constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, idx, ids, log_ray (< 0: not sampled)
-__host__ __device__ constexpr int ring_size(int P) { return P >= 512 ? 512 : 256; }
+__host__ __device__ constexpr int ring_size(int P) { return (P >= 512 && P <= 1152) ? 512 : 256; }
 __host__ __device__ constexpr size_t pool_bytes(int P) {
   return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + (size_t)ring_size(P) * 7 * 8 +
          64 /*counters*/;
@@ -140,7 +140,8 @@ __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
 }
 
 // counters (u32): [0..3], [4..7] queue lengths, double buffered by iteration parity; then the cursors of the slice
-enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrCount = 16 };
+enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrSteal = 12 /* [2]: stage 1, 2 */,
+       kCtrCount = 16 };
 
 struct PoolView {
   double *px, *py, *pz, *dx, *dy, *dz, *wl, *trav, *dur, *t, *u, *alpha;
@@ -225,10 +226,16 @@ __device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, l
   }
 }
 
-template <int T, int B, bool kLog>
+// take the next chunk of 32 work items of the current stage: one shared atomic per warp
+__device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
+  uint32_t c = 0;
+  if (lane == 0) c = atomicAdd(counter, 1u);
+  return __shfl_sync(kFullMask, c, 0);
+}
+
+// T threads per CTA, P pool slots (multiple of 32, typically ~2T), B resident CTAs per SM
+template <int T, int P, int B, bool kLog>
 __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
-  constexpr int P = T - 64;  // two warps own no slot: they produce fresh rays in stage 1 and absorb the warp
-                             // padding of the queues in stage 2
   constexpr int K = ring_size(P);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -248,130 +255,163 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
   const long long slice_hi = a.n * (long long)(blockIdx.x + 1) / gridDim.x;
   const uint32_t slice_n = (uint32_t)(slice_hi - slice_lo);
   if (tid < kCtrCount) pool.counters[tid] = 0u;
-  if (tid < P) pool.count[tid] = -1;
+  for (int s = tid; s < P; s += T) pool.count[s] = -1;
   __syncthreads();
 
   LaneStats st;
   for (uint32_t iter = 0;; ++iter) {
     uint32_t* qn = pool.counters + 4 * (iter & 1);
-    const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
-    // ---------------- stage 1: refill + classify (slot == tid); the spare warps produce rays ---------------
+    // ---------------- stage 1: refill + classify the pool, 32 slots per chunk; then produce fresh rays --------
+    // Every warp takes chunks from one shared counter until the stage's work list is empty, so no warp has a
+    // fixed share: classification chunks first (long), ray production chunks last (short).
     bool live = false;
-    if (tid < P) {
-      PoolPhoton ph;
-      const bool dead = pool.count[tid] < 0;
-      const unsigned m = __ballot_sync(kFullMask, dead);
-      bool fresh = false;
-      if (m) {
-        uint32_t base = 0;
-        const int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(pool.counters + kCtrNext, (uint32_t)__popc(m));
-        base = __shfl_sync(kFullMask, base, leader);
-        const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
-        if (dead && mine < slice_n) {
-          const long long i = slice_lo + mine;
-          if (mine < ring_hi) {
-            const double* r = pool.ring + (mine & (K - 1));
-            ph.p = V3{r[0], r[K], r[2 * K]};
-            ph.d = V3{r[3 * K], r[4 * K], r[5 * K]};
-            ph.wl = r[6 * K];
-          } else {
-            fetch_ray(a, sv, i, ph.p, ph.d, ph.wl);
-          }
-          ph.log_ray = (kLog && a.record_every > 0) ? sampled_ordinal(i, a.record_every) : -1;
-          ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
-          begin_photon<kLog>(ph, L, sp, st);
-          pool.idx[tid] = mine;
-          if (kLog) pool.log_ray[tid] = ph.log_ray;
-          pool.seen[tid] = 0ull;
-          fresh = true;
-        }
-      }
-      StepClass cls = kDead;
-      if (fresh || !dead) {
-        if (!fresh) load_slot_head<kLog>(pool, tid, ph, sp.max_events);
-        PhiloxStream rng;
-        rng.id = id0 + (u64)(slice_lo + pool.idx[tid]);
-        StepPlan plan;
-        cls = classify_step<kLog>(sv, L, sp, ph, rng, st, plan);
-        if (cls == kDead) {
-          if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
-          pool.count[tid] = -1;
-        } else {
-          if (fresh) store_slot<kLog>(pool, tid, ph);
-          pool.count[tid] = ph.count;
-          pool.t[tid] = plan.t; pool.u[tid] = plan.u; pool.alpha[tid] = plan.alpha;
-          pool.ids[tid] = (uint32_t)(plan.hit & 0xff) | ((uint32_t)(plan.container & 0xff) << 8) |
-                          ((uint32_t)(plan.adjacent & 0xff) << 16) | (cls == kKill ? 1u << 24 : 0u);
-          live = true;
-        }
-      }
-      push_queue(pool.qv, qn + 0, cls == kVolume, tid, lane);
-      push_queue(pool.qs, qn + 1, cls == kSurface, tid, lane);
-      push_queue(pool.qe, qn + 2, cls == kExit || cls == kKill, tid, lane);
-    } else {
-      // producer warps: rays [max(ring_hi, next), next + K) of the slice into the ring.  `next` is the snapshot
-      // taken at the last barrier, so the entries the consumers read in this stage are never overwritten.
+    {
+      const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
+      // rays to produce: [max(ring_hi, next), next + K), `next` being the snapshot taken at the last barrier, so
+      // ring entries read by this stage's refills are never overwritten
       const uint32_t next = pool.counters[kCtrNextSnap];
-      uint32_t lo = ring_hi > next ? ring_hi : next;
+      const uint32_t lo = ring_hi > next ? ring_hi : next;
       uint32_t hi = next + (uint32_t)K;
       if (hi > slice_n) hi = slice_n;
-      for (uint32_t o = lo + (uint32_t)(tid - P); o < hi; o += (uint32_t)(T - P)) {
-        V3 p, d;
-        double w;
-        const long long i = slice_lo + o;
-        if (a.pos) {
-          p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
-          d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
-          w = a.wl[i];
-        } else {
-          emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
-        }
-        double* r = pool.ring + (o & (K - 1));
-        r[0] = p.x; r[K] = p.y; r[2 * K] = p.z; r[3 * K] = d.x; r[4 * K] = d.y; r[5 * K] = d.z; r[6 * K] = w;
+      if (hi < lo) hi = lo;
+      const uint32_t classify_chunks = P / 32, ray_chunks = (hi - lo + 31u) >> 5;
+      if (tid == 0) {
+        pool.counters[kCtrRingHiPending] = hi;
+        pool.counters[kCtrSteal + 1] = 0u;  // stage 2's work counter
       }
-      if (tid == P) pool.counters[kCtrRingHiPending] = hi > lo ? hi : lo;
+      for (;;) {
+        const uint32_t chunk = steal_chunk(pool.counters + kCtrSteal, lane);
+        if (chunk >= classify_chunks + ray_chunks) break;
+        if (chunk < classify_chunks) {
+          const int slot = (int)(chunk * 32u) + lane;
+          PoolPhoton ph;
+          const bool dead = pool.count[slot] < 0;
+          const unsigned m = __ballot_sync(kFullMask, dead);
+          bool fresh = false;
+          if (m) {
+            uint32_t base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(pool.counters + kCtrNext, (uint32_t)__popc(m));
+            base = __shfl_sync(kFullMask, base, leader);
+            const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
+            if (dead && mine < slice_n) {
+              const long long i = slice_lo + mine;
+              if (mine < ring_hi) {
+                const double* r = pool.ring + (mine & (K - 1));
+                ph.p = V3{r[0], r[K], r[2 * K]};
+                ph.d = V3{r[3 * K], r[4 * K], r[5 * K]};
+                ph.wl = r[6 * K];
+              } else {
+                fetch_ray(a, sv, i, ph.p, ph.d, ph.wl);
+              }
+              ph.log_ray = (kLog && a.record_every > 0) ? sampled_ordinal(i, a.record_every) : -1;
+              ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
+              begin_photon<kLog>(ph, L, sp, st);
+              pool.idx[slot] = mine;
+              if (kLog) pool.log_ray[slot] = ph.log_ray;
+              pool.seen[slot] = 0ull;
+              fresh = true;
+            }
+          }
+          StepClass cls = kDead;
+          if (fresh || !dead) {
+            if (!fresh) load_slot_head<kLog>(pool, slot, ph, sp.max_events);
+            PhiloxStream rng;
+            rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
+            StepPlan plan;
+            cls = classify_step<kLog>(sv, L, sp, ph, rng, st, plan);
+            if (cls == kDead) {
+              if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
+              pool.count[slot] = -1;
+            } else {
+              if (fresh) store_slot<kLog>(pool, slot, ph);
+              pool.count[slot] = ph.count;
+              pool.t[slot] = plan.t; pool.u[slot] = plan.u; pool.alpha[slot] = plan.alpha;
+              pool.ids[slot] = (uint32_t)(plan.hit & 0xff) | ((uint32_t)(plan.container & 0xff) << 8) |
+                               ((uint32_t)(plan.adjacent & 0xff) << 16) | (cls == kKill ? 1u << 24 : 0u);
+              live = true;
+            }
+          }
+          push_queue(pool.qv, qn + 0, cls == kVolume, slot, lane);
+          push_queue(pool.qs, qn + 1, cls == kSurface, slot, lane);
+          push_queue(pool.qe, qn + 2, cls == kExit || cls == kKill, slot, lane);
+        } else {
+          const uint32_t o = lo + (chunk - classify_chunks) * 32u + (uint32_t)lane;
+          if (o < hi) {
+            V3 p, d;
+            double w;
+            const long long i = slice_lo + o;
+            if (a.pos) {
+              p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
+              d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
+              w = a.wl[i];
+            } else {
+              emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
+            }
+            double* r = pool.ring + (o & (K - 1));
+            r[0] = p.x; r[K] = p.y; r[2 * K] = p.z; r[3 * K] = d.x; r[4 * K] = d.y; r[5 * K] = d.z; r[6 * K] = w;
+          }
+        }
+      }
     }
     if (!__syncthreads_or(live)) break;
 
-    // ---------------- stage 2: interact, thread e serves queue entry e ------------------------------------
-    const int cv = (int)qn[0], cs = (int)qn[1], ce = (int)qn[2];
-    const int pv = (cv + 31) & ~31, ps = (cs + 31) & ~31;
+    // ---------------- stage 2: interact; chunks of 32 entries of the VOLUME, SURFACE, EXIT queues in that
+    // order (longest first), each chunk one kind of interaction with every lane busy ------------------------
+    const uint32_t cv = qn[0], cs = qn[1], ce = qn[2];
+    const uint32_t nv = (cv + 31u) >> 5, ns = (cs + 31u) >> 5, ne = (ce + 31u) >> 5;
     if (tid < 4) pool.counters[4 * ((iter + 1) & 1) + tid] = 0u;
     if (tid == T - 1) {  // publish the cursors for the next iteration (nobody refills or produces in stage 2)
       pool.counters[kCtrRingHi] = pool.counters[kCtrRingHiPending];
       pool.counters[kCtrNextSnap] = pool.counters[kCtrNext];
+      pool.counters[kCtrSteal] = 0u;  // stage 1's work counter
     }
-    int slot = -1, cls = kDead;
-    if (tid < pv) { if (tid < cv) { slot = pool.qv[tid]; cls = kVolume; } }
-    else if (tid < pv + ps) { if (tid - pv < cs) { slot = pool.qs[tid - pv]; cls = kSurface; } }
-    else if (tid - pv - ps < ce) { slot = pool.qe[tid - pv - ps]; cls = kExit; }
-    if (slot >= 0) {
-      PoolPhoton ph;
-      load_slot<kLog>(pool, slot, ph, sp.max_events);
-      PhiloxStream rng;
-      rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
-      rng.begin_step((uint32_t)ph.count);
-      StepPlan plan;
-      plan.t = pool.t[slot]; plan.u = pool.u[slot]; plan.alpha = pool.alpha[slot];
-      const uint32_t ids = pool.ids[slot];
-      plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
-      if (plan.adjacent == 0xff) plan.adjacent = -1;
-      bool alive = false;
-      TallyReq tr;
-      if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
-      else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
-      else if (ids >> 24) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
-      else exit_step<kLog>(sv, L, sp, ph, st, plan, tr);
-      if (alive) {
-        store_slot<kLog>(pool, slot, ph);
+    for (;;) {
+      uint32_t chunk = steal_chunk(pool.counters + kCtrSteal + 1, lane);
+      if (chunk >= nv + ns + ne) break;
+      int slot = -1, cls;
+      if (chunk < nv) {
+        cls = kVolume;
+        const uint32_t e = chunk * 32u + (uint32_t)lane;
+        if (e < cv) slot = pool.qv[e];
+      } else if (chunk < nv + ns) {
+        cls = kSurface;
+        const uint32_t e = (chunk - nv) * 32u + (uint32_t)lane;
+        if (e < cs) slot = pool.qs[e];
       } else {
-        if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
-        pool.count[slot] = -1;
+        cls = kExit;
+        const uint32_t e = (chunk - nv - ns) * 32u + (uint32_t)lane;
+        if (e < ce) slot = pool.qe[e];
       }
-      if (tr.sel >= 0) {
-        tally(sv, sink, ph, tr);
-        if (alive) pool.seen[slot] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);
+      if (slot >= 0) {
+        PoolPhoton ph;
+        load_slot<kLog>(pool, slot, ph, sp.max_events);
+        PhiloxStream rng;
+        rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
+        rng.begin_step((uint32_t)ph.count);
+        StepPlan plan;
+        plan.t = pool.t[slot]; plan.u = pool.u[slot]; plan.alpha = pool.alpha[slot];
+        const uint32_t ids = pool.ids[slot];
+        plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
+        if (plan.adjacent == 0xff) plan.adjacent = -1;
+        bool alive = false;
+        TallyReq tr;
+        if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+        else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+        else if (ids >> 24) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
+        else exit_step<kLog>(sv, L, sp, ph, st, plan, tr);
+        if (alive) {
+          store_slot<kLog>(pool, slot, ph);
+        } else {
+          if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
+          pool.count[slot] = -1;
+        }
+        // tallied in place: queueing the requests of the VOLUME / SURFACE chunks (few lanes each) to serve them 32
+        // at a time in the next stage 1 was measured slower (10.7 -> 11.7 ms on config 2), twice
+        if (tr.sel >= 0) {
+          tally(sv, sink, ph, tr);
+          if (alive) pool.seen[slot] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);
+        }
       }
     }
     __syncthreads();
