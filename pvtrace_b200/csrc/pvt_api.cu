@@ -291,6 +291,7 @@ extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const dou
   PVT_CUDA(cudaMemsetAsync(c->d_work(), 0, 8, st));
 
   TraceArgs a;
+  a.hdr = c->hdr;
   a.blob = c->blob.ptr; a.blob_words = c->blob_words; a.scene_in_smem = c->scene_in_smem;
   a.pos = have_rays ? d_pos : nullptr; a.dir = have_rays ? d_dir : nullptr; a.wl = have_rays ? d_wl : nullptr;
   a.n = P->n; a.first_index = P->first_index; a.record_every = P->record_every; a.seed = P->seed;

@@ -33,6 +33,7 @@ constexpr int kReservoirChunk = 64;  // photon indices a warp takes from the glo
 constexpr unsigned kFullMask = 0xffffffffu;
 
 struct TraceArgs {
+  Header hdr;          // copy of the blob's header (read as kernel-parameter constants)
   const double* blob;  // scene blob in global memory
   int blob_words;
   int scene_in_smem;   // 0: the blob did not fit into shared memory, read it through L1/L2 instead
@@ -235,13 +236,13 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
 
 // T threads per CTA, P pool slots (multiple of 32, typically ~2T), B resident CTAs per SM
 template <int T, int P, int B, bool kLog>
-__global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int K = ring_size(P);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
   stage_blob(sblob, a.blob, (uint32_t)a.blob_words * 8u, bar);
-  const SceneView sv{sblob};
+  const SceneView sv{sblob, &a.hdr};
   const PoolView pool = carve_pool(smem_raw + 16 + (size_t)a.blob_words * 8, P);
   const int R = sv.hdr().n_recorders;
   const TallySink sink = cta_sink(a, R);
@@ -426,12 +427,12 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const TraceArgs a) {
 __host__ __device__ inline size_t trace_smem_bytes(int blob_words_in_smem) { return 16 + (size_t)blob_words_in_smem * 8; }
 
 template <class Rng, int SW>
-__global__ void __launch_bounds__(kTraceThreads) trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(kTraceThreads) trace_kernel(const __grid_constant__ TraceArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
   if (a.scene_in_smem) stage_blob(sblob, a.blob, (uint32_t)a.blob_words * 8u, bar);
-  const SceneView sv{a.scene_in_smem ? sblob : a.blob};
+  const SceneView sv{a.scene_in_smem ? sblob : a.blob, &a.hdr};
   const int R = sv.hdr().n_recorders;
   const TallySink sink = cta_sink(a, R);
   const StepParams sp = a.sp;

@@ -187,8 +187,12 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
 #ifdef __CUDACC__
 // Read-only typed view over a blob held in shared (or, for oversized scenes, global) memory.
 struct SceneView {
-  const double* w;  // blob words
-  __device__ __forceinline__ const Header& hdr() const { return *reinterpret_cast<const Header*>(w); }
+  const double* w;   // blob words
+  const Header* h;   // the header: a copy in the kernel's parameter space when the kernel has one (offsets then come
+                     // from the constant bank, not from a dependent shared-memory load), else the blob's own
+  __device__ __forceinline__ SceneView(const double* words) : w(words), h(reinterpret_cast<const Header*>(words)) {}
+  __device__ __forceinline__ SceneView(const double* words, const Header* header) : w(words), h(header) {}
+  __device__ __forceinline__ const Header& hdr() const { return *h; }
   __device__ __forceinline__ int ival(int word, int half) const { return reinterpret_cast<const int32_t*>(w)[2 * word + half]; }
   __device__ __forceinline__ const double* node(int i) const { return w + hdr().off_nodes + i * kNodeWords; }
   __device__ __forceinline__ int node_int(int i, int k) const { return ival(hdr().off_nodes + i * kNodeWords + kNodeInts + (k >> 1), k & 1); }
