@@ -457,7 +457,7 @@ struct Timer {
   }
 };
 
-constexpr int kMaxChunks = 8;            // pieces a host bundle is uploaded + traced in
+constexpr int kMaxChunks = 16;           // pieces a host bundle is uploaded + traced in
 constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each
 
 // One cached context per process: bundles of the same scene (engine.simulate_stream, repeated simulate calls)
@@ -511,13 +511,35 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   PVT_CUDA(cudaEventRecord(t0, s_run));
   int rc = pvt_context_reset(c, s_run);
   const size_t n = (size_t)params->n;
-  if (!rc && have_rays && n > 0) {
+  // Page-locked host arrays (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are read by the kernel IN
+  // PLACE: the warps that fill the shared-memory ray ring pull them over PCIe with coalesced loads, a whole
+  // ring ahead of their use, so there is no separate upload and the trace runs at min(PCIe, kernel) speed.
+  const double *z_pos = nullptr, *z_dir = nullptr, *z_wl = nullptr;
+  if (!rc && have_rays && n > 0 && !(getenv("PVT_ZERO_COPY") && atoi(getenv("PVT_ZERO_COPY")) == 0)) {
+    const void* host[3] = {positions, directions, wavelengths};
+    const double* dev[3] = {nullptr, nullptr, nullptr};
+    bool all = true;
+    for (int k = 0; k < 3 && all; ++k) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, host[k]) != cudaSuccess) { cudaGetLastError(); all = false; break; }
+      all = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+      dev[k] = static_cast<const double*>(attr.devicePointer);
+    }
+    if (all) { z_pos = dev[0]; z_dir = dev[1]; z_wl = dev[2]; }
+  }
+  if (!rc && z_pos) {
+    rc = pvt_trace_device(c, z_pos, z_dir, z_wl, params, s_run);
+  } else if (!rc && have_rays && n > 0) {
     if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
     rc = g_rays.reserve(7 * n);
     double *d_pos = g_rays.ptr, *d_dir = g_rays.ptr + 3 * n, *d_wl = g_rays.ptr + 6 * n;
     // the event log is indexed by the ray's position in the bundle, so logged bundles go in one piece
     int chunks = (params->record_every == 0 && n >= (size_t)kMinChunkRays * 2) ? (int)(n / kMinChunkRays) : 1;
     if (chunks > kMaxChunks) chunks = kMaxChunks;
+    if (const char* env = getenv("PVT_UPLOAD_CHUNKS")) {  // tuning knob
+      const int want = atoi(env);
+      if (want >= 1 && want <= kMaxChunks && params->record_every == 0) chunks = want;
+    }
     for (int k = 0; k < chunks && !rc; ++k) {
       const size_t lo = n * k / chunks, hi = n * (k + 1) / chunks, m = hi - lo;
       cudaError_t e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);

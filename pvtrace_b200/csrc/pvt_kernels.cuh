@@ -281,8 +281,31 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         pool.counters[kCtrSteal + 1] = 0u;  // stage 2's work counter
       }
       for (;;) {
-        const uint32_t chunk = steal_chunk(pool.counters + kCtrSteal, lane);
+        uint32_t chunk = steal_chunk(pool.counters + kCtrSteal, lane);
         if (chunk >= classify_chunks + ray_chunks) break;
+        // Ray production first: its loads have the longest latency of the stage (HBM, or host memory over PCIe
+        // when the caller's arrays are page-locked) and the warp that waits for them simply takes fewer
+        // classification chunks afterwards (10.33 -> 10.19 ms on config 2 against producing last).
+        if (chunk < ray_chunks) {
+          const uint32_t o = lo + chunk * 32u + (uint32_t)lane;  // slice offset of this lane's ray
+          if (o < hi) {
+            V3 p, d;
+            double w;
+            const long long i = slice_lo + o;
+            if (a.pos) {
+              // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles)
+              p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
+              d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
+              w = a.wl[i];
+            } else {
+              emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
+            }
+            double* r = pool.ring + (o & (K - 1));
+            r[0] = p.x; r[K] = p.y; r[2 * K] = p.z; r[3 * K] = d.x; r[4 * K] = d.y; r[5 * K] = d.z; r[6 * K] = w;
+          }
+          continue;
+        }
+        chunk -= ray_chunks;
         if (chunk < classify_chunks) {
           const int slot = (int)(chunk * 32u) + lane;
           PoolPhoton ph;
@@ -336,22 +359,6 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
           push_queue(pool.qv, qn + 0, cls == kVolume, slot, lane);
           push_queue(pool.qs, qn + 1, cls == kSurface, slot, lane);
           push_queue(pool.qe, qn + 2, cls == kExit || cls == kKill, slot, lane);
-        } else {
-          const uint32_t o = lo + (chunk - classify_chunks) * 32u + (uint32_t)lane;
-          if (o < hi) {
-            V3 p, d;
-            double w;
-            const long long i = slice_lo + o;
-            if (a.pos) {
-              p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
-              d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
-              w = a.wl[i];
-            } else {
-              emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
-            }
-            double* r = pool.ring + (o & (K - 1));
-            r[0] = p.x; r[K] = p.y; r[2 * K] = p.z; r[3 * K] = d.x; r[4 * K] = d.y; r[5 * K] = d.z; r[6 * K] = w;
-          }
         }
       }
     }
