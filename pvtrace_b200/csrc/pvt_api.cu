@@ -47,6 +47,7 @@ struct pvt_context {
   DeviceBuffer<u64> tallies;
   size_t tally_words = 0;
   DeviceBuffer<double> packed;
+  DeviceBuffer<uint32_t> arrived;  // streaming-upload mark (see TraceArgs::arrived)
   DeviceBuffer<u64> slabs;  // CTA-private tally slabs of one launch: [max_grid][10 R]
   int max_grid = 0;
   int wave_threads = 0;     // CTA size of the wavefront kernel for this scene, 0: scene needs trace_kernel
@@ -191,6 +192,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   if (!rc) rc = c->packed.reserve((size_t)10 * c->R() + c->B() + 1);
   c->max_grid = c->sm_count * 8;
   if (!rc) rc = c->slabs.reserve((size_t)c->max_grid * 10 * c->R() + 1);
+  if (!rc) rc = c->arrived.reserve(4);
   if (!rc && cudaMemcpy(c->blob.ptr, c->host_blob.data(), (size_t)c->blob_words * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     rc = fail("scene upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (!rc && cudaMemset(c->tallies.ptr, 0, c->tally_words * 8) != cudaSuccess)
@@ -214,7 +216,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
 extern "C" int pvt_context_destroy(pvt_context_t* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  c->blob.release(); c->tallies.release(); c->packed.release(); c->slabs.release();
+  c->blob.release(); c->tallies.release(); c->packed.release(); c->slabs.release(); c->arrived.release();
   c->counts.release(); c->hit.release(); c->container.release(); c->adjacent.release(); c->component.release();
   c->source.release(); c->kind.release(); c->position.release(); c->direction.release(); c->normal.release();
   c->wavelength.release(); c->travelled.release(); c->duration.release();
@@ -278,8 +280,24 @@ static int check_params(const pvt_params_t* P) {
   return 0;
 }
 
+// CTAs of the wavefront kernel for a bundle of n rays, 0 when the bundle has to go through trace_kernel
+static int wave_grid(const pvt_context* c, const pvt_params_t* P) {
+  if (c->wave_threads <= 0 || P->rng_mode != PVT_RNG_PHILOX || (P->flags & PVT_FLAG_REGISTER_KERNEL) || P->n <= 0) return 0;
+  const long long want_blocks = (P->n + c->wave_pool - 1) / c->wave_pool;
+  const long long resident = (long long)c->sm_count * c->wave_ctas;
+  return (int)(want_blocks < resident ? want_blocks : resident);
+}
+
+static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
+                             const pvt_params_t* P, void* stream, const uint32_t* arrived);
+
 extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
                                 const pvt_params_t* P, void* stream) {
+  return trace_device_impl(c, d_pos, d_dir, d_wl, P, stream, nullptr);
+}
+
+static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
+                             const pvt_params_t* P, void* stream, const uint32_t* arrived) {
   if (!c) return fail("ctx is NULL");
   PVT_TRY(check_params(P));
   const bool have_rays = d_pos && d_dir && d_wl;
@@ -304,18 +322,17 @@ extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const dou
                      c->travelled.ptr, c->duration.ptr};
 
   a.slabs = c->slabs.ptr;
-  const bool megakernel_forced = (P->flags & PVT_FLAG_REGISTER_KERNEL) != 0;
-  int grid;
-  if (c->wave_threads > 0 && P->rng_mode == PVT_RNG_PHILOX && !megakernel_forced) {
-    // one persistent CTA per SM, each owning a contiguous slice of the photon range
-    const int pool = c->wave_pool;
-    const long long want_blocks = (P->n + pool - 1) / pool;
-    const long long resident = (long long)c->sm_count * c->wave_ctas;
-    grid = (int)(want_blocks < resident ? want_blocks : resident);
-    if (P->n / grid >= (1ll << 31)) return fail("bundle too large: at most 2^31 rays per resident CTA per call");
+  int grid = wave_grid(c, P);
+  a.arrived = arrived;
+  a.slice_pitch = 0;
+  if (grid > 0) {
+    // persistent CTAs, each owning a contiguous slice of `slice_pitch` photons
+    a.slice_pitch = (P->n + grid - 1) / grid;
+    if (a.slice_pitch >= (1ll << 31)) return fail("bundle too large: at most 2^31 rays per resident CTA per call");
     PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
     PVT_TRY(launch_wave(c, &a, grid, st));
   } else {
+    if (arrived) return fail("streaming upload needs the wavefront kernel");
     const int wide = c->R() > 64;
     const int which = (P->rng_mode == PVT_RNG_XOSHIRO ? 2 : 0) + wide;
     long long want_blocks = (P->n + kTraceThreads - 1) / kTraceThreads;
@@ -457,8 +474,9 @@ struct Timer {
   }
 };
 
-constexpr int kMaxChunks = 16;           // pieces a host bundle is uploaded + traced in
-constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each
+constexpr int kMaxChunks = 64;           // pieces a host bundle is uploaded + traced in
+constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each (separate launches)
+constexpr size_t kStreamChunkRays = 320000;  // chunk of the streaming upload (one launch, arrival marks)
 
 // One cached context per process: bundles of the same scene (engine.simulate_stream, repeated simulate calls)
 // reuse the uploaded blob and every device buffer.
@@ -511,11 +529,12 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   PVT_CUDA(cudaEventRecord(t0, s_run));
   int rc = pvt_context_reset(c, s_run);
   const size_t n = (size_t)params->n;
-  // Page-locked host arrays (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are read by the kernel IN
-  // PLACE: the warps that fill the shared-memory ray ring pull them over PCIe with coalesced loads, a whole
-  // ring ahead of their use, so there is no separate upload and the trace runs at min(PCIe, kernel) speed.
+  // Opt-in (PVT_ZERO_COPY=1): page-locked host arrays (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are
+  // read by the kernel IN PLACE, the warps that fill the shared-memory ray ring pulling them over PCIe a whole ring
+  // ahead of their use.  Measured 42-45 GB/s against the copy engine's 55 GB/s, so the streaming upload below
+  // is the default.
   const double *z_pos = nullptr, *z_dir = nullptr, *z_wl = nullptr;
-  if (!rc && have_rays && n > 0 && !(getenv("PVT_ZERO_COPY") && atoi(getenv("PVT_ZERO_COPY")) == 0)) {
+  if (!rc && have_rays && n > 0 && getenv("PVT_ZERO_COPY") && atoi(getenv("PVT_ZERO_COPY")) == 1) {
     const void* host[3] = {positions, directions, wavelengths};
     const double* dev[3] = {nullptr, nullptr, nullptr};
     bool all = true;
@@ -529,6 +548,54 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   }
   if (!rc && z_pos) {
     rc = pvt_trace_device(c, z_pos, z_dir, z_wl, params, s_run);
+  } else if (!rc && have_rays && n > 0 && wave_grid(c, params) > 0 &&
+             !(getenv("PVT_STREAM_UPLOAD") && atoi(getenv("PVT_STREAM_UPLOAD")) == 0)) {
+    // Streaming upload: the trace kernel starts at once and polls an arrival mark; the copy engine delivers, chunk
+    // by chunk, the next sub-block of EVERY CTA's slice (one strided 2-D copy per array) followed, in stream
+    // order, by the new mark.  Upload and trace overlap completely: total time ~ max(PCIe, kernel).
+    static uint32_t* h_marks = nullptr;  // page-locked: the mark copies must not be staged
+    if (!h_marks) PVT_CUDA(cudaHostAlloc((void**)&h_marks, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
+    if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
+    rc = g_rays.reserve(7 * n);
+    double *d_pos = g_rays.ptr, *d_dir = g_rays.ptr + 3 * n, *d_wl = g_rays.ptr + 6 * n;
+    const long long grid = wave_grid(c, params), S = ((long long)n + grid - 1) / grid;
+    int chunks = (int)(n / kStreamChunkRays);
+    chunks = chunks < 1 ? 1 : (chunks > kMaxChunks ? kMaxChunks : chunks);
+    if (const char* env = getenv("PVT_UPLOAD_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= kMaxChunks) chunks = v; }
+    const long long w = (S + chunks - 1) / chunks;
+    cudaError_t e = cudaSuccess;
+    if (!rc) e = cudaMemsetAsync(c->arrived.ptr, 0, 4, s_copy);
+    if (!rc && e == cudaSuccess) e = cudaEventRecord(s_uploaded[0], s_copy);
+    if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(s_run, s_uploaded[0], 0);
+    if (!rc && e == cudaSuccess) rc = trace_device_impl(c, d_pos, d_dir, d_wl, params, s_run, c->arrived.ptr);
+    for (int k = 0; k < chunks && !rc && e == cudaSuccess; ++k) {
+      const long long lo = (long long)k * w, wk = lo + w <= S ? w : S - lo;
+      if (wk <= 0) break;
+      // slices 0 .. full-1 hold at least lo + wk rays; slice `full` (the last non-empty one) may hold fewer
+      long long full = (long long)n >= lo + wk ? ((long long)n - (lo + wk)) / S + 1 : 0;
+      if (full > grid) full = grid;
+      if (full > 0) {
+        e = cudaMemcpy2DAsync(d_pos + 3 * lo, S * 24, positions + 3 * lo, S * 24, wk * 24, full, cudaMemcpyHostToDevice, s_copy);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync(d_dir + 3 * lo, S * 24, directions + 3 * lo, S * 24, wk * 24, full, cudaMemcpyHostToDevice, s_copy);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync(d_wl + lo, S * 8, wavelengths + lo, S * 8, wk * 8, full, cudaMemcpyHostToDevice, s_copy);
+      }
+      const long long tail_lo = full * S + lo, tail = (long long)n - tail_lo;  // partial row, < wk rays
+      if (e == cudaSuccess && full < grid && tail > 0 && tail < wk) {
+        e = cudaMemcpyAsync(d_pos + 3 * tail_lo, positions + 3 * tail_lo, tail * 24, cudaMemcpyHostToDevice, s_copy);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir + 3 * tail_lo, directions + 3 * tail_lo, tail * 24, cudaMemcpyHostToDevice, s_copy);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_wl + tail_lo, wavelengths + tail_lo, tail * 8, cudaMemcpyHostToDevice, s_copy);
+      }
+      h_marks[k] = (uint32_t)(lo + wk);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->arrived.ptr, h_marks + k, 4, cudaMemcpyHostToDevice, s_copy);
+    }
+    if (!rc && e != cudaSuccess) {
+      // never leave the kernel polling: publish "everything arrived" so it drains, then report
+      h_marks[kMaxChunks - 1] = 0xffffffffu;
+      cudaMemcpyAsync(c->arrived.ptr, h_marks + kMaxChunks - 1, 4, cudaMemcpyHostToDevice, s_copy);
+      rc = fail("ray upload failed: %s", cudaGetErrorString(e));
+    }
   } else if (!rc && have_rays && n > 0) {
     if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
     rc = g_rays.reserve(7 * n);
@@ -557,6 +624,11 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
     rc = pvt_trace_device(c, nullptr, nullptr, nullptr, params, s_run);
   }
   if (!rc) rc = pvt_context_read(c, out, s_run);
+  if (!rc && n > 0) {  // every ray must have been traced (a streaming upload that stalled would show up here)
+    u64 traced = 0;
+    if (cudaMemcpy(&traced, c->d_stats() + PVT_STAT_RAYS, 8, cudaMemcpyDeviceToHost) != cudaSuccess || traced != (u64)n)
+      rc = fail("traced %llu of %zu rays (upload did not complete?)", traced, n);
+  }
   if (!rc) {
     cudaError_t e = cudaEventRecord(t1, s_run);
     if (e == cudaSuccess) e = cudaEventSynchronize(t1);

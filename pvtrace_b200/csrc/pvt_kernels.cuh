@@ -31,12 +31,19 @@ namespace pvt {
 constexpr int kTraceThreads = 256;
 constexpr int kReservoirChunk = 64;  // photon indices a warp takes from the global counter at a time (>= 32)
 constexpr unsigned kFullMask = 0xffffffffu;
+constexpr uint32_t kMaxIdleIterations = 4000000u;  // ~ seconds of polling for host rays before a CTA gives up
 
 struct TraceArgs {
   Header hdr;          // copy of the blob's header (read as kernel-parameter constants)
   const double* blob;  // scene blob in global memory
   int blob_words;
   int scene_in_smem;   // 0: the blob did not fit into shared memory, read it through L1/L2 instead
+  // Streaming upload (wavefront kernel only): the kernel is launched BEFORE the host rays have arrived.  Photons
+  // are dealt to CTAs in contiguous slices of `slice_pitch`; the copy engine delivers the slices' next sub-blocks
+  // chunk by chunk and then stores, in stream order, how many rays of EVERY slice are complete into *arrived.
+  // A CTA never touches a ray at or beyond that mark.  arrived == nullptr: all rays are there.
+  const uint32_t* arrived;
+  long long slice_pitch;
   const double* pos;   // [n,3] or null (=> emit on device)
   const double* dir;
   const double* wl;
@@ -142,7 +149,7 @@ __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
 
 // counters (u32): [0..3], [4..7] queue lengths, double buffered by iteration parity; then the cursors of the slice
 enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrSteal = 12 /* [2]: stage 1, 2 */,
-       kCtrCount = 16 };
+       kCtrAvail = 14 /* rays of the slice that have arrived (snapshot taken at the last barrier) */, kCtrCount = 16 };
 
 struct PoolView {
   double *px, *py, *pz, *dx, *dy, *dz, *wl, *trav, *dur, *t, *u, *alpha;
@@ -219,9 +226,9 @@ __device__ __forceinline__ void push_queue(uint16_t* q, uint32_t* counter, bool 
 // fresh rays from the shared-memory ring that the spare warps keep filled
 __device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, long long i, V3& p, V3& d, double& wl) {
   if (a.pos) {
-    p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
-    d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
-    wl = a.wl[i];
+    p = V3{__ldcg(a.pos + 3 * i), __ldcg(a.pos + 3 * i + 1), __ldcg(a.pos + 3 * i + 2)};
+    d = V3{__ldcg(a.dir + 3 * i), __ldcg(a.dir + 3 * i + 1), __ldcg(a.dir + 3 * i + 2)};
+    wl = __ldcg(a.wl + i);
   } else {
     emit_ray(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i, p, d, wl);
   }
@@ -252,14 +259,16 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
 
   const int tid = threadIdx.x, lane = tid & 31;
   // contiguous slice of the photon range owned by this CTA
-  const long long slice_lo = a.n * (long long)blockIdx.x / gridDim.x;
-  const long long slice_hi = a.n * (long long)(blockIdx.x + 1) / gridDim.x;
+  long long slice_lo = a.slice_pitch * (long long)blockIdx.x;
+  if (slice_lo > a.n) slice_lo = a.n;
+  const long long slice_hi = slice_lo + a.slice_pitch < a.n ? slice_lo + a.slice_pitch : a.n;
   const uint32_t slice_n = (uint32_t)(slice_hi - slice_lo);
-  if (tid < kCtrCount) pool.counters[tid] = 0u;
+  if (tid < kCtrCount) pool.counters[tid] = (tid == kCtrAvail && !a.arrived) ? slice_n : 0u;
   for (int s = tid; s < P; s += T) pool.count[s] = -1;
   __syncthreads();
 
   LaneStats st;
+  uint32_t idle_iterations = 0;
   for (uint32_t iter = 0;; ++iter) {
     uint32_t* qn = pool.counters + 4 * (iter & 1);
     // ---------------- stage 1: refill + classify the pool, 32 slots per chunk; then produce fresh rays --------
@@ -272,8 +281,9 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
       // ring entries read by this stage's refills are never overwritten
       const uint32_t next = pool.counters[kCtrNextSnap];
       const uint32_t lo = ring_hi > next ? ring_hi : next;
+      const uint32_t avail = pool.counters[kCtrAvail];  // <= slice_n
       uint32_t hi = next + (uint32_t)K;
-      if (hi > slice_n) hi = slice_n;
+      if (hi > avail) hi = avail;
       if (hi < lo) hi = lo;
       const uint32_t classify_chunks = P / 32, ray_chunks = (hi - lo + 31u) >> 5;
       if (tid == 0) {
@@ -294,9 +304,10 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
             const long long i = slice_lo + o;
             if (a.pos) {
               // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles)
-              p = V3{a.pos[3 * i], a.pos[3 * i + 1], a.pos[3 * i + 2]};
-              d = V3{a.dir[3 * i], a.dir[3 * i + 1], a.dir[3 * i + 2]};
-              w = a.wl[i];
+              // (L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived)
+              p = V3{__ldcg(a.pos + 3 * i), __ldcg(a.pos + 3 * i + 1), __ldcg(a.pos + 3 * i + 2)};
+              d = V3{__ldcg(a.dir + 3 * i), __ldcg(a.dir + 3 * i + 1), __ldcg(a.dir + 3 * i + 2)};
+              w = __ldcg(a.wl + i);
             } else {
               emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
             }
@@ -315,10 +326,17 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
           if (m) {
             uint32_t base = 0;
             const int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(pool.counters + kCtrNext, (uint32_t)__popc(m));
+            if (lane == leader) {
+              // take popc(m) ray indices, but none at or beyond `avail`: what was taken in excess is given back
+              // (another warp may see the inflated cursor meanwhile and take less than it could -- its slots
+              // simply stay empty until the next iteration; indices below `avail` are handed out exactly once)
+              const uint32_t cnt = (uint32_t)__popc(m);
+              base = atomicAdd(pool.counters + kCtrNext, cnt);
+              if (base + cnt > avail) atomicSub(pool.counters + kCtrNext, base + cnt - (base > avail ? base : avail));
+            }
             base = __shfl_sync(kFullMask, base, leader);
             const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
-            if (dead && mine < slice_n) {
+            if (dead && mine < avail) {
               const long long i = slice_lo + mine;
               if (mine < ring_hi) {
                 const double* r = pool.ring + (mine & (K - 1));
@@ -362,7 +380,12 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         }
       }
     }
-    if (!__syncthreads_or(live)) break;
+    // leave when no slot is live and every ray of the slice has been taken; while rays are still in flight from
+    // the host the CTA keeps polling (bounded: a transfer that never completes must not hang the device)
+    const bool pending = pool.counters[kCtrNextSnap] < slice_n && idle_iterations < kMaxIdleIterations;
+    const bool any_live = __syncthreads_count(live) > 0;
+    if (!any_live && !pending) break;
+    idle_iterations = any_live ? 0u : idle_iterations + 1u;
 
     // ---------------- stage 2: interact; chunks of 32 entries of the VOLUME, SURFACE, EXIT queues in that
     // order (longest first), each chunk one kind of interaction with every lane busy ------------------------
@@ -372,6 +395,10 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     if (tid == T - 1) {  // publish the cursors for the next iteration (nobody refills or produces in stage 2)
       pool.counters[kCtrRingHi] = pool.counters[kCtrRingHiPending];
       pool.counters[kCtrNextSnap] = pool.counters[kCtrNext];
+      if (a.arrived) {
+        const uint32_t mark = *reinterpret_cast<const volatile uint32_t*>(a.arrived);
+        pool.counters[kCtrAvail] = mark < slice_n ? mark : slice_n;
+      }
       pool.counters[kCtrSteal] = 0u;  // stage 1's work counter
     }
     for (;;) {

@@ -22,22 +22,21 @@ for rep in range(3):
     dt = time.perf_counter() - t0
     print(f"H2D 560 MB pinned: {dt*1e3:.2f} ms  {0.56/dt:.1f} GB/s")
 arrs = [t.numpy() for t in h]
-for chunks in (1, 2, 4, 8, 16):
-    os.environ["PVT_UPLOAD_CHUNKS"] = str(chunks)
-    for rep in range(3):
-        t0 = time.perf_counter()
-        out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
-        dt = time.perf_counter() - t0
-    print(f"chunks={chunks:2d}: wall {dt*1e3:.2f} ms  device-elapsed {el*1e3:.2f} ms")
-os.environ.pop("PVT_UPLOAD_CHUNKS")
-for zc in ("0", "1"):
-    os.environ["PVT_ZERO_COPY"] = zc
-    for rep in range(4):
-        t0 = time.perf_counter()
-        out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
-        dt = time.perf_counter() - t0
-    print(f"zero_copy={zc}: wall {dt*1e3:.2f} ms  device-elapsed {el*1e3:.2f} ms  exit {out['rec_distinct'][0]}")
+for mode in ("stream", "copy"):
+    os.environ["PVT_STREAM_UPLOAD"] = "1" if mode == "stream" else "0"
+    for chunks in ((16, 32, 64) if mode == 'stream' else (4,)):
+        os.environ["PVT_UPLOAD_CHUNKS"] = str(chunks)
+        for rep in range(3):
+            t0 = time.perf_counter()
+            out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
+            dt = time.perf_counter() - t0
+        print(f"{mode} chunks={chunks:2d}: wall {dt*1e3:.2f} ms  device-elapsed {el*1e3:.2f} ms  exit {out['rec_distinct'][0]} rays {out['stats'][1]}")
+os.environ.pop("PVT_UPLOAD_CHUNKS"); os.environ["PVT_STREAM_UPLOAD"] = "1"
 pageable = [np.array(a) for a in arrs]
+for n_small in (1000, 12345, 2_000_003):
+    out = _cuda.trace_bundle(compiled, pageable[0][:n_small], pageable[1][:n_small], pageable[2][:n_small], 1, 1000, 128, 0, 0, 0)
+    ref = _cuda.trace_bundle(compiled, pageable[0][:n_small], pageable[1][:n_small], pageable[2][:n_small], 1, 1000, 128, 0, 0, 0, flags=1)
+    print(n_small, "stream == register kernel:", (out["rec_distinct"] == ref["rec_distinct"]).all(), out["stats"][1])
 for rep in range(3):
     t0 = time.perf_counter()
     out, el = _cuda.trace_bundle(compiled, pageable[0], pageable[1], pageable[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
