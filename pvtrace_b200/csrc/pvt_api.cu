@@ -478,6 +478,20 @@ constexpr int kMaxChunks = 64;           // pieces a host bundle is uploaded + t
 constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each (separate launches)
 constexpr size_t kStreamChunkRays = 320000;  // chunk of the streaming upload (one launch, arrival marks)
 
+// The streaming upload needs the copy stream to make progress WHILE the trace kernel runs.  Anything that
+// serialises the two (CUDA_LAUNCH_BLOCKING, a profiler replaying kernels one at a time) would leave the kernel
+// polling until it gives up, so the path is switched off when such a tool is detected, when the user says so
+// (PVT_STREAM_UPLOAD=0), and for good after a bundle that did not complete (which is then re-traced the plain way).
+bool g_stream_upload_ok = true;
+bool stream_upload_allowed() {
+  if (!g_stream_upload_ok) return false;
+  if (const char* env = getenv("PVT_STREAM_UPLOAD")) return atoi(env) != 0;
+  if (const char* env = getenv("CUDA_LAUNCH_BLOCKING")) { if (atoi(env) != 0) return false; }
+  if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NVTX_INJECTION64_PATH"))
+    return false;
+  return true;
+}
+
 // One cached context per process: bundles of the same scene (engine.simulate_stream, repeated simulate calls)
 // reuse the uploaded blob and every device buffer.
 std::mutex g_cache_mutex;
@@ -533,6 +547,7 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   // read by the kernel IN PLACE, the warps that fill the shared-memory ray ring pulling them over PCIe a whole ring
   // ahead of their use.  Measured 42-45 GB/s against the copy engine's 55 GB/s, so the streaming upload below
   // is the default.
+  bool streamed = false;
   const double *z_pos = nullptr, *z_dir = nullptr, *z_wl = nullptr;
   if (!rc && have_rays && n > 0 && getenv("PVT_ZERO_COPY") && atoi(getenv("PVT_ZERO_COPY")) == 1) {
     const void* host[3] = {positions, directions, wavelengths};
@@ -548,11 +563,11 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   }
   if (!rc && z_pos) {
     rc = pvt_trace_device(c, z_pos, z_dir, z_wl, params, s_run);
-  } else if (!rc && have_rays && n > 0 && wave_grid(c, params) > 0 &&
-             !(getenv("PVT_STREAM_UPLOAD") && atoi(getenv("PVT_STREAM_UPLOAD")) == 0)) {
+  } else if (!rc && have_rays && n > 0 && wave_grid(c, params) > 0 && stream_upload_allowed()) {
     // Streaming upload: the trace kernel starts at once and polls an arrival mark; the copy engine delivers, chunk
     // by chunk, the next sub-block of EVERY CTA's slice (one strided 2-D copy per array) followed, in stream
     // order, by the new mark.  Upload and trace overlap completely: total time ~ max(PCIe, kernel).
+    streamed = true;
     static uint32_t* h_marks = nullptr;  // page-locked: the mark copies must not be staged
     if (!h_marks) PVT_CUDA(cudaHostAlloc((void**)&h_marks, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
     if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
@@ -624,10 +639,20 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
     rc = pvt_trace_device(c, nullptr, nullptr, nullptr, params, s_run);
   }
   if (!rc) rc = pvt_context_read(c, out, s_run);
-  if (!rc && n > 0) {  // every ray must have been traced (a streaming upload that stalled would show up here)
+  if (!rc && n > 0) {  // every ray must have been traced
     u64 traced = 0;
-    if (cudaMemcpy(&traced, c->d_stats() + PVT_STAT_RAYS, 8, cudaMemcpyDeviceToHost) != cudaSuccess || traced != (u64)n)
-      rc = fail("traced %llu of %zu rays (upload did not complete?)", traced, n);
+    if (cudaMemcpy(&traced, c->d_stats() + PVT_STAT_RAYS, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      rc = fail("reading the ray counter failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else if (traced != (u64)n && streamed) {
+      // the kernel gave up polling for rays: something serialised upload and trace.  Trace again the plain way.
+      g_stream_upload_ok = false;
+      cudaStreamSynchronize(s_copy);
+      rc = pvt_context_reset(c, s_run);
+      if (!rc) rc = pvt_trace_device(c, g_rays.ptr, g_rays.ptr + 3 * n, g_rays.ptr + 6 * n, params, s_run);
+      if (!rc) rc = pvt_context_read(c, out, s_run);
+    } else if (traced != (u64)n) {
+      rc = fail("traced %llu of %zu rays", traced, n);
+    }
   }
   if (!rc) {
     cudaError_t e = cudaEventRecord(t1, s_run);

@@ -1,6 +1,7 @@
 """The engine API on the device (mirrors the reference's tests/test_engine.py): exact self-consistency of tallies
 with the engine's own event log, invariance to record_every / bundle splitting / kernel choice, on-device emission,
 the intersect stage, the facet (coating) table, and size-independent invariants at BASELINE's full photon counts."""
+import functools
 import os
 
 import numpy as np
@@ -229,3 +230,76 @@ def test_validation_scene_against_published_fractions(gpu):
     lost = rec["LSC-lost"].rays / n
     edge = (rec["LSC-east"].rays + rec["LSC-west"].rays + rec["LSC-north"].rays + rec["LSC-south"].rays) / n
     assert abs(edge - 0.25) < 0.04 and abs(lost - 0.11) < 0.04          # test_3D_flux_comparison.py:78-106
+
+
+def test_host_ray_upload_paths_agree(gpu, monkeypatch):
+    """pvt_trace_bundle with HOST arrays: the streaming upload (kernel follows arrival marks), the chunked plain upload
+    and device-resident emission of the same rays must give identical integer tallies, for sizes around the chunking /
+    slicing boundaries."""
+    from pvtrace_b200.engine.emit import emit_bundle
+
+    scene = configs.lsc_default()
+    compiled = pv.engine.compile_scene(scene)
+    for n in (1, 31, 1000, 148 * 1024 + 5, 700001):
+        pos, direction, wl, _ = emit_bundle(scene, n, seed=21)
+        results = []
+        for mode in ("1", "0"):
+            monkeypatch.setenv("PVT_STREAM_UPLOAD", mode)
+            results.append(_cuda.trace_bundle(compiled, pos, direction, wl, 21, 1000, 128, 0, 0, 0))
+        monkeypatch.delenv("PVT_STREAM_UPLOAD")
+        emitted = _cuda.trace_bundle(compiled, None, None, None, 21, 1000, 128, 0, 0, 0,
+                                     emitter=pv.engine.compile_emitter(scene), n=n)
+        for other in (results[1], emitted):
+            for key in ("rec_distinct", "rec_crossings", "rec_bins"):
+                assert (results[0][key] == other[key]).all(), (n, key)
+        assert results[0]["stats"][_cuda.STAT_RAYS] == n
+        assert results[0]["rec_distinct"][:2].sum() == n  # exit + lost
+
+
+def test_empty_and_tiny_bundles(gpu):
+    scene = scenes.lsc()
+    result = pv.engine.simulate(scene, 0, seed=1)
+    assert result.num_rays == 0 and result.num_recorded == 0 and result.recorders["exit"].rays == 0
+    result = pv.engine.simulate(scene, 1, seed=1, record_every=1)
+    assert result.num_recorded == 1 and result.data["counts"][0] >= 2
+    assert result.recorders["exit"].rays + result.recorders["lost"].rays == 1
+    # event budget: a sampled ray that runs out of log rows ends with KILL (pvtrace/engine/_kernel.pyx:658-663)
+    result = pv.engine.simulate(scenes.lsc(), 2000, seed=2, record_every=1, max_events=4)
+    counts = result.data["counts"]
+    kinds = result.data["kind"].reshape(-1, 4)
+    killed = (kinds == Event.KILL.value).any(axis=1)
+    assert counts.max() == 4 and killed.sum() > 500
+    assert (counts[killed] == 4).all() and (kinds[killed][:, 3] == Event.KILL.value).all()
+    want = pvt_oracle.trace_bundle(result.compiled, None, None, None, 2, 1000, 4, 0, 2, 1,
+                                   emitter=pv.engine.compile_emitter(scenes.lsc()), n=2000)
+    assert (want["counts"] == counts).mean() > 0.999 and (want["kind"] == result.data["kind"]).mean() > 0.999
+
+
+def test_maxsteps_kill_is_tallied(gpu):
+    """A perfect mirror box traps light: rays die by KILL at count > maxsteps and the `killed` recorder sees them
+    (pvtrace/engine/_kernel.pyx:716-723)."""
+    from pvtrace_b200 import Facet, FacetSurfaceDelegate
+
+    world = pv.Node(name="world", geometry=pv.Sphere(10.0, material=pv.Material(1.0)))
+    mirror = pv.Surface(delegate=FacetSurfaceDelegate([Facet(n, reflectivity=1.0) for n in
+                                                       ((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1))]))
+    cage = pv.Node(name="cage", parent=world, geometry=pv.Box((2.0, 2.0, 2.0), material=pv.Material(1.0, surface=mirror)))
+    pv.Node(name="light", parent=world, light=pv.Light(direction=functools.partial(pv.cone, 0.3)))
+    cage.recorders.append(pv.engine.Recorder("killed", event="killed"))
+    world.recorders.append(pv.engine.Recorder("exit", event="exit"))
+    for flags in (0, _cuda.FLAG_REGISTER_KERNEL):
+        compiled, emitter = pv.engine.compile_scene(pv.Scene(world)), pv.engine.compile_emitter(pv.Scene(world))
+        out = _cuda.trace_bundle(compiled, None, None, None, 3, 50, 128, 0, 0, 0, emitter=emitter, n=5000, flags=flags)
+        assert out["rec_distinct"].tolist() == [0, 5000]  # [exit, killed]: nothing leaves the cage
+        assert out["stats"][_cuda.STAT_STEPS] == 5000 * 51
+
+
+def test_custom_light_delegate_falls_back_to_host_emission(gpu):
+    world = pv.Node(name="world", geometry=pv.Sphere(10.0, material=pv.Material(1.0)))
+    pv.Node(name="ball", parent=world, geometry=pv.Sphere(1.0, material=pv.Material(1.5))).location = (0, 0, 3)
+    pv.Node(name="lamp", parent=world, light=pv.Light(direction=lambda: (0.0, 0.0, 1.0), name="lamp"))
+    world.recorders.append(pv.engine.Recorder("exit", event="exit"))
+    result = pv.engine.simulate(pv.Scene(world), 500, seed=1)
+    assert result.recorders["exit"].rays == 500 and result.sources[0] == "lamp"
+    first = next(iter(result.histories()))
+    assert first[0][0].direction == (0.0, 0.0, 1.0) and first[0][0].source == "lamp"
