@@ -548,23 +548,37 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const __grid_const
 // ---- the intersect stage on its own ----------------------------------------------------------------------
 // 60 B of algorithmic traffic per ray: reads position + direction (48 B), writes t0 (8 B) and three int32 ids
 // (12 B; SURVEY 8d counts them packed as 4 B).
-__global__ void __launch_bounds__(256) intersect_kernel(const double* blob, int blob_words, int scene_in_smem,
-                                                        const double* pos, const double* dir, long long n, double* t0,
-                                                        int32_t* hit, int32_t* container, int32_t* adjacent) {
+template <int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas) intersect_kernel(const __grid_constant__ Header hdr, const double* blob,
+                                                           int blob_words, int scene_in_smem, const double* pos,
+                                                           const double* dir, long long n, double* t0, int32_t* hit,
+                                                           int32_t* container, int32_t* adjacent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
   if (scene_in_smem) stage_blob(sblob, blob, (uint32_t)blob_words * 8u, bar);
-  const SceneView sv{scene_in_smem ? sblob : blob};
+  const SceneView sv{scene_in_smem ? sblob : blob, &hdr};
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const V3 p = V3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
-    const V3 d = V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // software pipeline: the next ray's six words are in flight while this one is intersected (streaming loads and
+  // stores: every byte is touched once)
+  V3 p = V3{__ldcs(pos + 3 * i), __ldcs(pos + 3 * i + 1), __ldcs(pos + 3 * i + 2)};
+  V3 d = V3{__ldcs(dir + 3 * i), __ldcs(dir + 3 * i + 1), __ldcs(dir + 3 * i + 2)};
+  for (;;) {
+    const long long j = i + stride;
+    V3 pn = p, dn = d;
+    if (j < n) {
+      pn = V3{__ldcs(pos + 3 * j), __ldcs(pos + 3 * j + 1), __ldcs(pos + 3 * j + 2)};
+      dn = V3{__ldcs(dir + 3 * j), __ldcs(dir + 3 * j + 1), __ldcs(dir + 3 * j + 2)};
+    }
     const Nearest nh = nearest_surface(sv, p, d);
-    t0[i] = nh.total ? nh.t0 : PVT_INF;
-    hit[i] = nh.total ? nh.hit : -1;
-    container[i] = nh.container;
-    adjacent[i] = nh.adjacent;
+    __stcs(t0 + i, nh.total ? nh.t0 : PVT_INF);
+    __stcs(hit + i, nh.total ? nh.hit : -1);
+    __stcs(container + i, nh.container);
+    __stcs(adjacent + i, nh.adjacent);
+    if (j >= n) break;
+    i = j; p = pn; d = dn;
   }
 }
 

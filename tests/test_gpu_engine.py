@@ -303,3 +303,22 @@ def test_custom_light_delegate_falls_back_to_host_emission(gpu):
     assert result.recorders["exit"].rays == 500 and result.sources[0] == "lamp"
     first = next(iter(result.histories()))
     assert first[0][0].direction == (0.0, 0.0, 1.0) and first[0][0].source == "lamp"
+
+
+def test_python_tracer_statistics_agree_with_device(gpu):
+    """tests/test_engine.py:139-166 on the device: Welch 5-sigma agreement of per-ray event-count means between the
+    reference PYTHON tracer (photon_tracer.follow; fixtures tests/golden/python_tracer_*.npz generated from the
+    unmodified reference) and the CUDA engine, and no ray of the engine run hits the event budget."""
+    for name in ("hello_world", "nested_cylinders"):
+        g = np.load(os.path.join(GOLDEN, f"python_tracer_{name}.npz"))
+        py = g["counts"].astype(float)
+        n, m = 20000, 256
+        result = pv.engine.simulate(scenes.SCENES[name](), n, seed=5, record_every=1, max_events=m)
+        counts = result.data["counts"]
+        assert (counts >= m - 1).mean() < 1e-3
+        kinds = result.data["kind"].reshape(n, m)
+        valid = np.arange(m)[None, :] < counts[:, None]
+        for ev in range(10):
+            mine = ((kinds == ev) & valid).sum(axis=1).astype(float)
+            se = np.sqrt(py[:, ev].var(ddof=1) / len(py) + mine.var(ddof=1) / n)
+            assert abs(py[:, ev].mean() - mine.mean()) <= 5 * se + 1e-12, (name, ev, py[:, ev].mean(), mine.mean())
