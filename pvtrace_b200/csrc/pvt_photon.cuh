@@ -60,59 +60,93 @@ struct Nearest {
   int hit, container, adjacent, total;
 };
 
-// next_hit + find_container (photon_tracer.py:26-109 == _kernel.pyx:666-714) as a single pass over the nodes:
-// keeps the two nearest roots overall and the nearest root among nodes hit exactly once.  Ties resolve to the
-// lowest node index (strict '<'), like the reference's scans.
+// next_hit + find_container (photon_tracer.py:26-109 == _kernel.pyx:666-714) as a single pass over the nodes that
+// keeps the two nearest roots overall and the nearest root among nodes hit exactly once.  The reduction is branch
+// free (selects on validity flags); ties resolve to the lowest node index (strict '<'), like the reference's scans.
+struct TwoNearest {
+  double t_first, t_second, t_single;
+  int n_first, n_second, n_single;
+  __device__ __forceinline__ TwoNearest()
+      : t_first(PVT_INF), t_second(PVT_INF), t_single(PVT_INF), n_first(-1), n_second(-1), n_single(-1) {}
+  // the reference's insertion: a root becomes the nearest if it beats it (or is the first one), else the second
+  // nearest if it beats that (or is the second one); +inf sentinels make "is the first / second one" implicit
+  __device__ __forceinline__ void add(double t, int node, bool ok) {
+    const bool lt1 = ok && t < t_first;
+    const bool lt2 = ok && !lt1 && t < t_second;
+    t_second = lt1 ? t_first : (lt2 ? t : t_second);
+    n_second = lt1 ? n_first : (lt2 ? node : n_second);
+    t_first = lt1 ? t : t_first;
+    n_first = lt1 ? node : n_first;
+  }
+  // a node with exactly one root: candidate container
+  __device__ __forceinline__ void add_single(double t, int node, bool ok) {
+    const bool lt = ok && t < t_single;
+    t_single = lt ? t : t_single;
+    n_single = lt ? node : n_single;
+  }
+};
+
 __device__ __forceinline__ Nearest nearest_surface(const SceneView& sv, const V3& p, const V3& d) {
   const int n_nodes = sv.hdr().n_nodes;
-  double t_first = PVT_INF, t_second = PVT_INF, t_single = PVT_INF;
-  int n_first = -1, n_second = -1, n_single = -1, total = 0;
+  TwoNearest best;
   V3 inv_world;           // 1 / d, shared by every axis-aligned box (their local direction IS d)
   bool have_inv = false;
   for (int node = 0; node < n_nodes; ++node) {
     const double* rec = sv.node(node);
     const int gtype = sv.node_int(node, NI_GEOM);
-    double ts[4];
-    int k;
+    V3 o, dl;
     if (sv.node_int(node, NI_ALIGNED)) {
       // rotation part of w2l is the identity: o = p + translation exactly as the full product would give
-      const V3 o = V3{p.x + rec[kNodeW2L + 3], p.y + rec[kNodeW2L + 7], p.z + rec[kNodeW2L + 11]};
-      if (gtype == 0) {
-        if (!have_inv) { inv_world = slab_reciprocal(d); have_inv = true; }
-        k = roots_box(rec[kNodeParams], rec[kNodeParams + 1], rec[kNodeParams + 2], o, d, inv_world, ts);
-      } else {
-        k = roots(gtype, rec + kNodeParams, o, d, ts);
-      }
+      o = V3{p.x + rec[kNodeW2L + 3], p.y + rec[kNodeW2L + 7], p.z + rec[kNodeW2L + 11]};
+      dl = d;
     } else {
-      const V3 o = map_point(rec + kNodeW2L, p);
-      const V3 dl = map_vector(rec + kNodeW2L, d);
-      k = roots(gtype, rec + kNodeParams, o, dl, ts);
+      o = map_point(rec + kNodeW2L, p);
+      dl = map_vector(rec + kNodeW2L, d);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (j < k) {
-        const double t = ts[j];
-        if (total == 0 || t < t_first) {
-          t_second = t_first; n_second = n_first;
-          t_first = t; n_first = node;
-        } else if (n_second < 0 || t < t_second) {
-          t_second = t; n_second = node;
-        }
-        ++total;
+    if (gtype == 0) {
+      V3 inv;
+      if (sv.node_int(node, NI_ALIGNED)) {
+        if (!have_inv) { inv_world = slab_reciprocal(d); have_inv = true; }
+        inv = inv_world;
+      } else {
+        inv = slab_reciprocal(dl);
       }
+      double t_in, t_out;
+      bool ok_in, ok_out;
+      box_roots(rec[kNodeParams], rec[kNodeParams + 1], rec[kNodeParams + 2], o, dl, inv, t_in, t_out, ok_in, ok_out);
+      best.add(t_in, node, ok_in);
+      best.add(t_out, node, ok_out);
+      best.add_single(t_out, node, ok_out && !ok_in);  // one root: it is the exit
+    } else if (gtype == 1) {
+      double t1, t2;
+      bool ok1, ok2;
+      sphere_roots(rec[kNodeParams], o, dl, t1, t2, ok1, ok2);
+      best.add(t1, node, ok1);
+      best.add(t2, node, ok2);
+      best.add_single(t2, node, ok2 && !ok1);
+    } else {
+      const Roots r = cylinder_roots(rec[kNodeParams], rec[kNodeParams + 1], o, dl);
+      int count = 0;
+      double only = PVT_INF;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        best.add(r.t[k], node, r.ok[k]);
+        count += r.ok[k] ? 1 : 0;
+        only = r.ok[k] ? r.t[k] : only;
+      }
+      best.add_single(only, node, count == 1);
     }
-    if (k == 1 && ts[0] < t_single) { t_single = ts[0]; n_single = node; }
   }
   Nearest r;
-  r.total = total;
-  r.t0 = t_first;
-  r.hit = n_first;
-  if (total <= 1) {
-    r.container = n_first;
+  r.total = best.n_first < 0 ? 0 : (best.n_second < 0 ? 1 : 2);  // 0, 1, "2 or more"
+  r.t0 = best.t_first;
+  r.hit = best.n_first;
+  if (r.total <= 1) {
+    r.container = best.n_first;
     r.adjacent = -1;
   } else {
-    r.container = n_single >= 0 ? n_single : n_first;
-    r.adjacent = r.container == n_first ? n_second : n_first;
+    r.container = best.n_single >= 0 ? best.n_single : best.n_first;
+    r.adjacent = r.container == best.n_first ? best.n_second : best.n_first;
   }
   return r;
 }
