@@ -113,11 +113,9 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
 
 // (threads, pool slots, resident CTAs per SM), preferred first; the first that fits the scene's shared memory wins
 struct WaveVariant { int threads, pool, ctas; };
-constexpr int kWaveVariants = 14;
-static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {640, 1152, 1}, {1024, 1024, 1}, {768, 1024, 1},
-                                                      {512, 768, 1},  {640, 640, 1},  {512, 512, 1},   {512, 512, 2},
-                                                      {384, 768, 1},  {256, 512, 1},  {512, 1280, 1},  {640, 1280, 1},
-                                                      {576, 1152, 1}, {448, 1344, 1}};
+constexpr int kWaveVariants = 6;
+static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {512, 896, 1}, {512, 768, 1},
+                                                      {512, 512, 1},  {384, 768, 1}, {256, 512, 1}};
 
 template <class K>
 static int wave_attr(K kernel, size_t smem) {
@@ -137,10 +135,8 @@ static int wave_attr(K kernel, size_t smem) {
     return 0;                                                                                    \
   }
 static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
-  PVT_WAVE_CASE(1024, 1024, 1) PVT_WAVE_CASE(768, 1024, 1) PVT_WAVE_CASE(640, 1152, 1) PVT_WAVE_CASE(640, 640, 1)
-  PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(512, 768, 1) PVT_WAVE_CASE(512, 512, 1) PVT_WAVE_CASE(512, 512, 2)
-  PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1) PVT_WAVE_CASE(512, 1280, 1) PVT_WAVE_CASE(640, 1280, 1)
-  PVT_WAVE_CASE(576, 1152, 1) PVT_WAVE_CASE(448, 1344, 1)
+  PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(512, 896, 1) PVT_WAVE_CASE(512, 768, 1) PVT_WAVE_CASE(512, 512, 1)
+  PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1)
   return fail("no wavefront kernel variant for %d threads / %d slots x %d CTAs", c->wave_threads, c->wave_pool, c->wave_ctas);
 }
 

@@ -139,9 +139,11 @@ __device__ __noinline__ int sampled_ordinal(long long i, long long record_every)
 constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
 constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, idx, ids, log_ray (< 0: not sampled)
 __host__ __device__ constexpr int ring_size(int P) { return (P >= 512 && P <= 1152) ? 512 : 256; }
+// Shared memory left over is L1: the kernel is sensitive to it (24 KB more of shared memory cost 5 %), so the pool
+// carries nothing it does not need.
 __host__ __device__ constexpr size_t pool_bytes(int P) {
   return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + (size_t)ring_size(P) * 7 * 8 +
-         64 /*counters*/;
+         128 /*counters*/;
 }
 __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
   return 16 + (size_t)blob_words * 8 + pool_bytes(P);
@@ -299,20 +301,17 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         if (chunk < ray_chunks) {
           const uint32_t o = lo + chunk * 32u + (uint32_t)lane;  // slice offset of this lane's ray
           if (o < hi) {
-            V3 p, d;
-            double w;
             const long long i = slice_lo + o;
-            if (a.pos) {
-              // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles)
-              // (L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived)
-              p = V3{__ldcg(a.pos + 3 * i), __ldcg(a.pos + 3 * i + 1), __ldcg(a.pos + 3 * i + 2)};
-              d = V3{__ldcg(a.dir + 3 * i), __ldcg(a.dir + 3 * i + 1), __ldcg(a.dir + 3 * i + 2)};
-              w = __ldcg(a.wl + i);
-            } else {
-              emit_ray(sv, id0 + (u64)i, a.first_index + i, p, d, w);
-            }
             double* r = pool.ring + (o & (K - 1));
-            r[0] = p.x; r[K] = p.y; r[2 * K] = p.z; r[3 * K] = d.x; r[4 * K] = d.y; r[5 * K] = d.z; r[6 * K] = w;
+            if (a.pos) {
+              // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles);
+              // L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived
+              r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2);
+              r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2);
+              r[6 * K] = __ldcg(a.wl + i);
+            } else {
+              emit_ray_to_ring(sv, id0 + (u64)i, a.first_index + i, r, K);
+            }
           }
           continue;
         }
@@ -344,7 +343,11 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
                 ph.d = V3{r[3 * K], r[4 * K], r[5 * K]};
                 ph.wl = r[6 * K];
               } else {
-                fetch_ray(a, sv, i, ph.p, ph.d, ph.wl);
+                // (through temporaries: taking the address of ph's fields would pin the whole photon in local memory)
+                V3 tp, td;
+                double tw;
+                fetch_ray(a, sv, i, tp, td, tw);
+                ph.p = tp; ph.d = td; ph.wl = tw;
               }
               ph.log_ray = (kLog && a.record_every > 0) ? sampled_ordinal(i, a.record_every) : -1;
               ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
@@ -441,8 +444,11 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
           if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
           pool.count[slot] = -1;
         }
-        // tallied in place: queueing the requests of the VOLUME / SURFACE chunks (few lanes each) to serve them 32
-        // at a time in the next stage 1 was measured slower (10.7 -> 11.7 ms on config 2), twice
+        // Tallied in place, by the few lanes of the chunk that have something to tally (~5 active lanes; a quarter
+        // of the kernel's issue slots).  Queueing these requests to serve them 32 at a time in the next stage 1 cut
+        // the instruction count by 8 % but was SLOWER every time it was tried (10.7 -> 11.7, 9.1 -> 11.1 ms on config
+        // 2): the extra short chunks break the two-rounds-per-warp balance of the stage (barrier stalls 9 % -> 23 %)
+        // and the queue's shared memory comes out of L1.
         if (tr.sel >= 0) {
           tally(sv, sink, ph, tr);
           if (alive) pool.seen[slot] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);

@@ -234,11 +234,20 @@ __device__ __forceinline__ SeenMask<SW> tally_event(const SceneView& sv, const T
     if (r < 0) break;
     ++k;
     red_add(&T.cross[r], 1ull);
-    const uint32_t bit = 1u << (r & 31);
-    bool was_seen = false;
+    bool was_seen;
+    if (SW == 2) {  // 64 recorders: two scalar words, no indexing
+      const uint32_t bit = 1u << (r & 31);
+      const bool high = r >= 32;
+      was_seen = ((high ? seen.w[1] : seen.w[0]) & bit) != 0;
+      seen.w[0] |= high ? 0u : bit;
+      seen.w[SW - 1] |= high ? bit : 0u;
+    } else {
+      const uint32_t bit = 1u << (r & 31);
+      was_seen = false;
 #pragma unroll
-    for (int w = 0; w < SW; ++w)
-      if (w == (r >> 5)) { was_seen = (seen.w[w] & bit) != 0; seen.w[w] |= bit; }
+      for (int w = 0; w < SW; ++w)
+        if (w == (r >> 5)) { was_seen = (seen.w[w] & bit) != 0; seen.w[w] |= bit; }
+    }
     if (was_seen) continue;
     if (angle < 0.0) angle = cosine >= 1.0 ? 0.0 : acos(cosine);
     red_add(&T.distinct[r], 1ull);
@@ -545,7 +554,28 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
 
 // ---- on-device emission of the built-in light delegates (emit.py:22-134; scene.py:141-151) ---------------
 // Uniform k of Philox stream kStreamEmit of ray id: k=0 wavelength, k=1..3 position, k=4,5 direction.
+struct EmittedRay {
+  V3 pos, dir;
+  double wl;
+};
+__device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, u64 id, long long index);
+
+// out-of-line forms: by reference (refill fallback, register kernel, emit_kernel) and straight into the columns of a
+// shared-memory ring of stride K (so the caller keeps nothing address-taken on its stack)
 __device__ __noinline__ void emit_ray(const SceneView sv, u64 id, long long index, V3& pos, V3& dir, double& wl) {
+  const EmittedRay r = emit_ray_value(sv, id, index);
+  pos = r.pos; dir = r.dir; wl = r.wl;
+}
+__device__ __noinline__ void emit_ray_to_ring(const SceneView sv, u64 id, long long index, double* dst, int K) {
+  const EmittedRay r = emit_ray_value(sv, id, index);
+  dst[0] = r.pos.x; dst[K] = r.pos.y; dst[2 * K] = r.pos.z;
+  dst[3 * K] = r.dir.x; dst[4 * K] = r.dir.y; dst[5 * K] = r.dir.z;
+  dst[6 * K] = r.wl;
+}
+
+__device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, u64 id, long long index) {
+  V3 pos, dir;
+  double wl;
   const Header& H = sv.hdr();
   const int l = (int)(index % H.n_lights);
   const double* q = sv.light(l);
@@ -605,6 +635,7 @@ __device__ __noinline__ void emit_ray(const SceneView sv, u64 id, long long inde
   }
   pos = map_point(q + kLightL2W, lp);
   dir = map_vector(q + kLightL2W, ld);
+  return EmittedRay{pos, dir, wl};
 }
 
 }  // namespace pvt
