@@ -113,8 +113,8 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
 
 // (threads, pool slots, resident CTAs per SM), preferred first; the first that fits the scene's shared memory wins
 struct WaveVariant { int threads, pool, ctas; };
-constexpr int kWaveVariants = 6;
-static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {512, 896, 1}, {512, 768, 1},
+constexpr int kWaveVariants = 7;
+static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {480, 960, 1}, {448, 896, 1}, {512, 768, 1},
                                                       {512, 512, 1},  {384, 768, 1}, {256, 512, 1}};
 
 template <class K>
@@ -135,8 +135,8 @@ static int wave_attr(K kernel, size_t smem) {
     return 0;                                                                                    \
   }
 static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
-  PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(512, 896, 1) PVT_WAVE_CASE(512, 768, 1) PVT_WAVE_CASE(512, 512, 1)
-  PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1)
+  PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(480, 960, 1) PVT_WAVE_CASE(448, 896, 1) PVT_WAVE_CASE(512, 768, 1)
+  PVT_WAVE_CASE(512, 512, 1) PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1)
   return fail("no wavefront kernel variant for %d threads / %d slots x %d CTAs", c->wave_threads, c->wave_pool, c->wave_ctas);
 }
 

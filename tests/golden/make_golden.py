@@ -281,7 +281,41 @@ def make_python_tracer_goldens():
                             event_names=np.array([e.name for e in kinds]))
 
 
+def make_yaml_goldens():
+    """Tables (and light poses / emitted rays) of the scenes the REFERENCE's YAML front end (pvtrace/cli/parse.py)
+    builds from the fixtures in tests/data/: what pvtrace_b200.cli.parse must reproduce."""
+    import pvtrace as pkg  # the stub top-level package: give it the names pvtrace/cli/parse.py imports from it
+    import pvtrace.geometry.mesh  # noqa: F401
+    for name, mod in (("Scene", "pvtrace.scene.scene"), ("Node", "pvtrace.scene.node"), ("Box", "pvtrace.geometry.box"),
+                      ("Mesh", "pvtrace.geometry.mesh"), ("Cylinder", "pvtrace.geometry.cylinder"),
+                      ("Sphere", "pvtrace.geometry.sphere"), ("Material", "pvtrace.material.material"),
+                      ("Absorber", "pvtrace.material.component"), ("Scatterer", "pvtrace.material.component"),
+                      ("Luminophore", "pvtrace.material.component"), ("Light", "pvtrace.light.light")):
+        __import__(mod)
+        setattr(pkg, name, getattr(sys.modules[mod], name))
+    pkg.MeshcatRenderer = object
+    import pvtrace.cli.parse as refparse
+
+    for stem in ("lsc_recorded", "primitives"):
+        scene = refparse.parse(os.path.join(ROOT, "tests", "data", stem + ".yml"))
+        compiled = compile_scene(scene)
+        tables = {t: np.asarray(getattr(compiled, t)) for t in TABLES}
+        tables["root_id"] = np.int64(compiled.root_id)
+        tables["total_bins"] = np.int64(compiled.total_bins)
+        tables["node_names"] = np.array(compiled.node_names)
+        tables["component_names"] = np.array(compiled.component_names)
+        tables["recorder_names"] = np.array(compiled.recorder_names)
+        lights = scene.light_nodes
+        tables["light_names"] = np.array([n.name for n in lights])
+        tables["light_to_world"] = np.array([np.asarray(n.transformation_to(scene.root)) for n in lights])
+        tables["light_delegates"] = np.array(["|".join(type(d).__name__ if not callable(getattr(d, "__name__", None)) else d.__name__
+                                                        for d in (n.light.wavelength, n.light.position, n.light.direction))
+                                              for n in lights])
+        np.savez_compressed(os.path.join(HERE, f"yaml_{stem}.npz"), **tables)
+
+
 if __name__ == "__main__":
+    make_yaml_goldens()
     make_optics()
     make_geometry()
     make_distribution()

@@ -322,3 +322,18 @@ def test_python_tracer_statistics_agree_with_device(gpu):
             mine = ((kinds == ev) & valid).sum(axis=1).astype(float)
             se = np.sqrt(py[:, ev].var(ddof=1) / len(py) + mine.var(ddof=1) / n)
             assert abs(py[:, ev].mean() - mine.mean()) <= 5 * se + 1e-12, (name, ev, py[:, ev].mean(), mine.mean())
+
+
+def test_yaml_scene_runs_on_the_device(gpu):
+    """tests/test_engine.py:374-415: a `record: true` scene parsed from YAML traces and tallies."""
+    from pvtrace_b200.cli.parse import parse
+
+    scene = parse(os.path.join(os.path.dirname(__file__), "data", "lsc_recorded.yml"))
+    result = pv.engine.simulate(scene, 20000, seed=2, record_every=0)
+    rec = result.recorders
+    assert rec["lsc-top"].rays > 0 and rec["lsc-lost"].rays > 0 and rec["edge-escape"].rays == rec["lsc-east"].rays
+    assert rec["lsc-top"].histogram(2)[-1].shape == (50, 50)
+    scene = parse(os.path.join(os.path.dirname(__file__), "data", "primitives.yml"))
+    result = pv.engine.simulate(scene, 30000, seed=3, record_every=100)
+    assert result.stats["rays"] == 30000 and set(result.sources[:3]) == {"lamp", "panel", "spot"}
+    assert result.recorders["rod-in"].rays > 0
