@@ -337,3 +337,26 @@ def test_yaml_scene_runs_on_the_device(gpu):
     result = pv.engine.simulate(scene, 30000, seed=3, record_every=100)
     assert result.stats["rays"] == 30000 and set(result.sources[:3]) == {"lamp", "panel", "spot"}
     assert result.recorders["rod-in"].rays > 0
+
+
+def test_stream_from_worker_thread_is_additive(gpu):
+    """The studio contract (pvtrace/studio/server.py:225-237): simulate_stream driven from a worker thread, tallies of
+    the bundles add up to the single-call result."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    scene = scenes.lsc()
+    whole = pv.engine.simulate(scene, 30000, seed=4, record_every=0).data
+
+    def run():
+        total = None
+        for result, traced in pv.engine.simulate_stream(scene, 30000, bundle=7000, seed=4, record_every=1000):
+            d = result.data
+            total = {k: d[k].copy() for k in ("rec_distinct", "rec_crossings", "rec_bins")} if total is None else \
+                {k: total[k] + d[k] for k in total}
+        return total, traced
+
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        total, traced = pool.submit(run).result()
+    assert traced == 30000
+    for key in total:
+        assert (total[key] == whole[key]).all(), key
