@@ -215,21 +215,30 @@ struct SeenMask {
 // none to six -- looked up in the blob's index; lanes search independently and update together.
 template <int SW>
 __device__ __forceinline__ SeenMask<SW> tally_event(const SceneView& sv, const TallySink& T, SeenMask<SW> seen, int sel,
-                                                    int node, bool has_normal, const V3& wnormal, const V3& lp,
-                                                    double cosine, double wl, double duration, double travelled) {
-  int k, k_end;
-  sv.rec_range(node, sel, k, k_end);
+                                                    int node, int face, bool has_normal, const V3& wnormal,
+                                                    const V3& lp, double cosine, double wl, double duration,
+                                                    double travelled) {
+  // Box faces have their matching recorders resolved on the host (the facet test against the face's world normal
+  // does not depend on the event); everything else searches the recorders of (node, selector).
+  int k, k_end = -1;
+  if (face >= 0) sv.face_range(node, sel, face, k, k_end);
+  const bool resolved = k_end >= 0;
+  if (!resolved) sv.rec_range(node, sel, k, k_end);
   k_end += k;
   double angle = -1.0;
   for (;;) {
     int r = -1;
-    for (; k < k_end; ++k) {
-      const int cand = sv.rec_candidate(k);
-      if (!sv.rec_int(cand, RI_HAS_FACET)) { r = cand; break; }
-      if (!has_normal) continue;
-      const double* q = sv.rec(cand);
-      const double tol = q[kRecAtol];
-      if (fabs(q[0] - wnormal.x) <= tol && fabs(q[1] - wnormal.y) <= tol && fabs(q[2] - wnormal.z) <= tol) { r = cand; break; }
+    if (resolved) {
+      if (k < k_end) r = sv.face_candidate(k);
+    } else {
+      for (; k < k_end; ++k) {
+        const int cand = sv.rec_candidate(k);
+        if (!sv.rec_int(cand, RI_HAS_FACET)) { r = cand; break; }
+        if (!has_normal) continue;
+        const double* q = sv.rec(cand);
+        const double tol = q[kRecAtol];
+        if (fabs(q[0] - wnormal.x) <= tol && fabs(q[1] - wnormal.y) <= tol && fabs(q[2] - wnormal.z) <= tol) { r = cand; break; }
+      }
     }
     if (r < 0) break;
     ++k;
@@ -281,6 +290,7 @@ __device__ __forceinline__ SeenMask<SW> tally_event(const SceneView& sv, const T
 struct TallyReq {
   int sel = -1;  // PVT_REC_*, < 0: nothing to tally
   int node;
+  int face = -1;  // box face of a surface event (pre-resolved recorder list), -1: search with the facet test
   bool has_normal;
   V3 normal, lp;
   double cosine;
@@ -292,8 +302,8 @@ __device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P
   SeenMask<SW> seen;
 #pragma unroll
   for (int k = 0; k < SW; ++k) seen.w[k] = ph.seen[k];
-  seen = tally_event<SW>(sv, T, seen, tr.sel, tr.node, tr.has_normal, tr.normal, tr.lp, tr.cosine, ph.wl, ph.duration,
-                         ph.travelled);
+  seen = tally_event<SW>(sv, T, seen, tr.sel, tr.node, tr.face, tr.has_normal, tr.normal, tr.lp, tr.cosine, ph.wl,
+                         ph.duration, ph.travelled);
 #pragma unroll
   for (int k = 0; k < SW; ++k) ph.seen[k] = seen.w[k];
 }
@@ -410,11 +420,12 @@ __device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns&
   if (sv.hdr().n_recorders > 0) {
     const double* rec = sv.node(hit);
     const V3 lp = map_point(rec + kNodeW2L, ph.p);
-    const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), rec + kNodeParams, lp);
+    int face;
+    const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), rec + kNodeParams, lp, face);
     const V3 nw = map_vector(rec + kNodeL2W, nl);
     double c = fabs(dot(nw, ph.d));
     if (c > 1.0) c = 1.0;
-    tr.sel = PVT_REC_EXIT; tr.node = hit; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c;
+    tr.sel = PVT_REC_EXIT; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c;
   }
 }
 
@@ -507,7 +518,8 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
   }
   const double* hrec = sv.node(hit);
   const V3 lp = map_point(hrec + kNodeW2L, ph.p);
-  const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), hrec + kNodeParams, lp);
+  int face;
+  const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), hrec + kNodeParams, lp, face);
   const V3 nw = map_vector(hrec + kNodeL2W, nl);
   V3 nf = nw;
   if (dot(nf, ph.d) < 0.0) nf = neg(nf);
@@ -548,7 +560,7 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
     PVT_LOG_N(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, true, nw);
     sel = container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING;
   }
-  if (record) { tr.sel = sel; tr.node = hit; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c; }
+  if (record) { tr.sel = sel; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c; }
   return true;
 }
 

@@ -18,6 +18,11 @@
 //   rec_index   n_nodes x kRecSelectors (start, count) int pairs into rec_list: the recorders attached to
 //               (node, selector), so a tally looks at its handful of candidates instead of every recorder
 //   rec_list    n_recorders int32 recorder indices grouped by (node, selector), original order within a group
+//   face_index  n_nodes x kRecSelectors x 6 (start, count) int pairs into face_list: for BOX nodes, the recorders
+//               of (node, selector) that match a surface event on local face f (-x +x -y +y -z +z) -- the facet
+//               test against the face's world normal is done once here instead of per event; count < 0 marks a
+//               node whose faces cannot be pre-resolved (not a box, or a facet within 1e-9 of its tolerance)
+//   face_list   int32 recorder indices
 #pragma once
 #include <stdint.h>
 #include <string.h>
@@ -30,7 +35,8 @@ namespace pvt {
 struct Header {
   int32_t n_nodes, root_id, n_components, n_recorders, n_hists, total_bins, n_facets, n_lights;
   int32_t off_nodes, off_comps, off_abs_x, off_abs_y, off_ems_x, off_ems_cdf, off_recs, off_hists;
-  int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, off_rec_index, off_rec_list, pad2;
+  int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, off_rec_index, off_rec_list, off_face_index;
+  int32_t off_face_list, pad3, pad4, pad5;
 };
 constexpr int kHeaderWords = sizeof(Header) / 8;
 static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
@@ -93,6 +99,9 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
   h.off_wl_cdf = w;  w += E ? E->n_wl_knots : 0;
   h.off_rec_index = w; w += S.n_nodes * kRecSelectors;
   h.off_rec_list = w;  w += (S.n_recorders + 1) / 2;
+  h.off_face_index = w; w += S.n_nodes * kRecSelectors * 6;
+  // worst case every recorder of a node matches all six faces
+  h.off_face_list = w; w += (6 * S.n_recorders + 1) / 2;
   w = (w + 1) & ~1;
   h.total_words = w;
 
@@ -177,6 +186,45 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
         put_ints(blob, h.off_rec_index + (size_t)node * kRecSelectors + sel, start, filled - start);
       }
   }
+  {
+    int32_t* list = reinterpret_cast<int32_t*>(&blob[h.off_face_list]);
+    int32_t filled = 0;
+    for (int node = 0; node < S.n_nodes; ++node) {
+      const double* m = S.local_to_world + 16 * node;
+      bool resolvable = S.geom_type[node] == PVT_GEOM_BOX;
+      // a facet whose distance to a face normal is within 1e-9 of its tolerance could go either way on the device
+      for (int f = 0; f < 6 && resolvable; ++f) {
+        const double sg = (f & 1) ? 1.0 : -1.0;
+        const int ax = f >> 1;
+        const double nw[3] = {m[ax] * sg, m[4 + ax] * sg, m[8 + ax] * sg};
+        for (int r = 0; r < S.n_recorders; ++r) {
+          if (S.rec_node[r] != node || !S.rec_has_facet[r]) continue;
+          for (int k = 0; k < 3; ++k) {
+            const double gap = fabs(S.rec_facet[3 * r + k] - nw[k]) - S.rec_atol[r];
+            if (fabs(gap) < 1e-9) resolvable = false;
+          }
+        }
+      }
+      for (int sel = 0; sel < kRecSelectors; ++sel)
+        for (int f = 0; f < 6; ++f) {
+          const size_t word = h.off_face_index + ((size_t)node * kRecSelectors + sel) * 6 + f;
+          if (!resolvable) { put_ints(blob, word, 0, -1); continue; }
+          const double sg = (f & 1) ? 1.0 : -1.0;
+          const int ax = f >> 1;
+          const double nw[3] = {m[ax] * sg, m[4 + ax] * sg, m[8 + ax] * sg};
+          const int32_t start = filled;
+          for (int r = 0; r < S.n_recorders; ++r) {
+            if (S.rec_node[r] != node || S.rec_event[r] != sel) continue;
+            bool match = true;
+            if (S.rec_has_facet[r])
+              for (int k = 0; k < 3; ++k)
+                if (fabs(S.rec_facet[3 * r + k] - nw[k]) > S.rec_atol[r]) match = false;
+            if (match) list[filled++] = r;
+          }
+          put_ints(blob, word, start, filled - start);
+        }
+    }
+  }
   if (E && E->n_wl_knots) {
     memcpy(&blob[h.off_wl_x], E->wl_x, E->n_wl_knots * sizeof(double));
     memcpy(&blob[h.off_wl_cdf], E->wl_cdf, E->n_wl_knots * sizeof(double));
@@ -210,6 +258,12 @@ struct SceneView {
     start = ival(word, 0); count = ival(word, 1);
   }
   __device__ __forceinline__ int rec_candidate(int k) const { return reinterpret_cast<const int32_t*>(w + hdr().off_rec_list)[k]; }
+  // recorders matching a surface event on local face `face` of a box node; count < 0: not pre-resolved
+  __device__ __forceinline__ void face_range(int node, int sel, int face, int& start, int& count) const {
+    const int word = hdr().off_face_index + (node * kRecSelectors + sel) * 6 + face;
+    start = ival(word, 0); count = ival(word, 1);
+  }
+  __device__ __forceinline__ int face_candidate(int k) const { return reinterpret_cast<const int32_t*>(w + hdr().off_face_list)[k]; }
   __device__ __forceinline__ const double* light(int l) const { return w + hdr().off_lights + l * kLightWords; }
   __device__ __forceinline__ int light_int(int l, int k) const { return ival(hdr().off_lights + l * kLightWords + kLightInts + (k >> 1), k & 1); }
 };
