@@ -38,6 +38,7 @@ def build(force=False, verbose=False):
         return LIB
     cmd = [nvcc_path(), *ARCH, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
            "-Xcompiler", "-O2", "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
+    cmd[1:1] = os.environ.get("PVT_NVCC_FLAGS", "").split()  # e.g. -DPVT_PROFILE_STAGES (tools/stage_profile.sh)
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)

@@ -53,6 +53,7 @@ struct pvt_context {
   int wave_threads = 0;     // CTA size of the wavefront kernel for this scene, 0: scene needs trace_kernel
   int wave_pool = 0;        // photon slots per CTA
   int wave_ctas = 1;        // resident CTAs per SM
+  bool wave_boxes = false;  // every node is an axis-aligned box: the kBoxes instantiation (no primitive switch)
   size_t wave_smem = 0;
   // event log of the last trace
   long long log_rows = 0, log_rays = 0;
@@ -113,9 +114,17 @@ static int occupancy(K kernel, size_t smem, int* blocks) {
 
 // (threads, pool slots, resident CTAs per SM), preferred first; the first that fits the scene's shared memory wins
 struct WaveVariant { int threads, pool, ctas; };
+#ifdef PVT_SWEEP  // extra shapes for tools/sweep.sh experiments (selected with PVT_WAVEFRONT_* in the environment)
+constexpr int kWaveVariants = 11;
+#else
 constexpr int kWaveVariants = 7;
+#endif
 static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {480, 960, 1}, {448, 896, 1}, {512, 768, 1},
-                                                      {512, 512, 1},  {384, 768, 1}, {256, 512, 1}};
+                                                      {512, 512, 1},  {384, 768, 1}, {256, 512, 1},
+#ifdef PVT_SWEEP
+                                                      {256, 512, 2}, {640, 1280, 1}, {768, 768, 1}, {1024, 1024, 1},
+#endif
+};
 
 template <class K>
 static int wave_attr(K kernel, size_t smem) {
@@ -127,16 +136,27 @@ static int wave_attr(K kernel, size_t smem) {
 #define PVT_WAVE_CASE(T, P, B)                                                                   \
   if (c->wave_threads == T && c->wave_pool == P && c->wave_ctas == B) {                          \
     if (!args) {                                                                                 \
-      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false>, c->wave_smem));                        \
-      return wave_attr(wavefront_kernel<T, P, B, true>, c->wave_smem);                           \
+      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, false>, c->wave_smem));                 \
+      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, true>, c->wave_smem));                  \
+      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, false>, c->wave_smem));                  \
+      return wave_attr(wavefront_kernel<T, P, B, true, true>, c->wave_smem);                     \
     }                                                                                            \
-    if (args->record_every > 0) wavefront_kernel<T, P, B, true><<<grid, T, c->wave_smem, st>>>(*args);  \
-    else wavefront_kernel<T, P, B, false><<<grid, T, c->wave_smem, st>>>(*args);                 \
+    const bool log = args->record_every > 0;                                                     \
+    if (c->wave_boxes) {                                                                         \
+      if (log) wavefront_kernel<T, P, B, true, true><<<grid, T, c->wave_smem, st>>>(*args);      \
+      else wavefront_kernel<T, P, B, false, true><<<grid, T, c->wave_smem, st>>>(*args);         \
+    } else {                                                                                     \
+      if (log) wavefront_kernel<T, P, B, true, false><<<grid, T, c->wave_smem, st>>>(*args);     \
+      else wavefront_kernel<T, P, B, false, false><<<grid, T, c->wave_smem, st>>>(*args);        \
+    }                                                                                            \
     return 0;                                                                                    \
   }
 static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
   PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(480, 960, 1) PVT_WAVE_CASE(448, 896, 1) PVT_WAVE_CASE(512, 768, 1)
   PVT_WAVE_CASE(512, 512, 1) PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1)
+#ifdef PVT_SWEEP
+  PVT_WAVE_CASE(256, 512, 2) PVT_WAVE_CASE(640, 1280, 1) PVT_WAVE_CASE(768, 768, 1) PVT_WAVE_CASE(1024, 1024, 1)
+#endif
   return fail("no wavefront kernel variant for %d threads / %d slots x %d CTAs", c->wave_threads, c->wave_pool, c->wave_ctas);
 }
 
@@ -166,6 +186,13 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   c->smem_bytes = trace_smem_bytes(c->scene_in_smem ? c->blob_words : 0);
   // wavefront kernel: needs the blob AND the photon pool in shared memory, <= 64 recorders (seen mask), <= 254 nodes
   c->wave_threads = 0;
+  c->wave_boxes = !getenv("PVT_NO_BOX_KERNEL");
+  for (int i = 0; i < scene->n_nodes; ++i) {
+    const double* m = scene->world_to_local + 16 * i;
+    const bool aligned = m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[4] == 0.0 && m[5] == 1.0 && m[6] == 0.0 &&
+                         m[8] == 0.0 && m[9] == 0.0 && m[10] == 1.0;
+    if (scene->geom_type[i] != PVT_GEOM_BOX || !aligned) c->wave_boxes = false;
+  }
   if (c->R() <= 64) {
     int want_t = 0, want_p = 0, want_b = 0;  // 0: any
     if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) want_t = atoi(env);

@@ -138,7 +138,7 @@ __device__ __noinline__ int sampled_ordinal(long long i, long long record_every)
 // three u16 queues; then the ring of prefetched initial rays (7 f64 columns of K entries) and the counters.
 constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
 constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, idx, ids, log_ray (< 0: not sampled)
-__host__ __device__ constexpr int ring_size(int P) { return (P >= 512 && P <= 1152) ? 512 : 256; }
+__host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 1152) ? 512 : 256; }
 // Shared memory left over is L1: the kernel is sensitive to it (24 KB more of shared memory cost 5 %), so the pool
 // carries nothing it does not need.
 __host__ __device__ constexpr size_t pool_bytes(int P) {
@@ -244,7 +244,7 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
 }
 
 // T threads per CTA, P pool slots (multiple of 32, typically ~2T), B resident CTAs per SM
-template <int T, int P, int B, bool kLog>
+template <int T, int P, int B, bool kLog, bool kBoxes = false>
 __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int K = ring_size(P);
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -271,6 +271,12 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
 
   LaneStats st;
   uint32_t idle_iterations = 0;
+#ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
+  long long prof[4] = {0, 0, 0, 0}, prof_t = clock64();
+#define PVT_PROF(k) do { const long long now_ = clock64(); prof[k] += now_ - prof_t; prof_t = now_; } while (0)
+#else
+#define PVT_PROF(k) do { } while (0)
+#endif
   for (uint32_t iter = 0;; ++iter) {
     uint32_t* qn = pool.counters + 4 * (iter & 1);
     // ---------------- stage 1: refill + classify the pool, 32 slots per chunk; then produce fresh rays --------
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
             PhiloxStream rng;
             rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
             StepPlan plan;
-            cls = classify_step<kLog>(sv, L, sp, ph, rng, st, plan);
+            cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan);
             if (cls == kDead) {
               if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
               pool.count[slot] = -1;
@@ -386,7 +392,9 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     // leave when no slot is live and every ray of the slice has been taken; while rays are still in flight from
     // the host the CTA keeps polling (bounded: a transfer that never completes must not hang the device)
     const bool pending = pool.counters[kCtrNextSnap] < slice_n && idle_iterations < kMaxIdleIterations;
+    PVT_PROF(0);
     const bool any_live = __syncthreads_count(live) > 0;
+    PVT_PROF(1);
     if (!any_live && !pending) break;
     idle_iterations = any_live ? 0u : idle_iterations + 1u;
 
@@ -455,8 +463,14 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         }
       }
     }
+    PVT_PROF(2);
     __syncthreads();
+    PVT_PROF(3);
   }
+#ifdef PVT_PROFILE_STAGES
+  if (tid == 0)
+    for (int k = 0; k < 4; ++k) atomicAdd(a.g_stats + 4 + k, (u64)prof[k]);
+#endif
   retire_cta(a, R, st);
 }
 

@@ -55,14 +55,14 @@ struct PhotonT {
 
 enum StepClass { kDead = 0, kExit = 1, kVolume = 2, kSurface = 3, kKill = 4 };  // kKill: step budget exhausted
 
+// next_hit + find_container (photon_tracer.py:26-109 == _kernel.pyx:666-714) as a single pass over the nodes that
+// keeps the two nearest roots overall and the nearest root among nodes hit exactly once.  The reduction is branch
+// free (selects on validity flags); ties resolve to the lowest node index (strict '<'), like the reference's scans.
 struct Nearest {
   double t0;
   int hit, container, adjacent, total;
 };
 
-// next_hit + find_container (photon_tracer.py:26-109 == _kernel.pyx:666-714) as a single pass over the nodes that
-// keeps the two nearest roots overall and the nearest root among nodes hit exactly once.  The reduction is branch
-// free (selects on validity flags); ties resolve to the lowest node index (strict '<'), like the reference's scans.
 struct TwoNearest {
   double t_first, t_second, t_single;
   int n_first, n_second, n_single;
@@ -78,11 +78,42 @@ struct TwoNearest {
     t_first = lt1 ? t : t_first;
     n_first = lt1 ? node : n_first;
   }
+  // Both roots of a box or a sphere at once: a <= b whenever both count, and a counts only if b does.  The same
+  // outcome as add(a) followed by add(b) (ties keep the earlier entry, strict '<') with three compares.
+  __device__ __forceinline__ void add_pair(double a, double b, int node, bool ok_a, bool ok_b) {
+    const double x = ok_a ? a : b;  // the nearer valid root (valid iff ok_b), b being the farther one (valid iff ok_a)
+    const bool x_first = ok_b && x < t_first;
+    const bool y_first = ok_a && b < t_first;
+    const bool x_second = ok_b && x < t_second;
+    const double t_keep = x_second ? x : t_second, t_push = y_first ? b : t_first;
+    const int n_keep = x_second ? node : n_second, n_push = y_first ? node : n_first;
+    t_second = x_first ? t_push : t_keep;
+    n_second = x_first ? n_push : n_keep;
+    t_first = x_first ? x : t_first;
+    n_first = x_first ? node : n_first;
+    add_single(b, node, ok_b && !ok_a);  // one root: it is the exit
+  }
   // a node with exactly one root: candidate container
   __device__ __forceinline__ void add_single(double t, int node, bool ok) {
     const bool lt = ok && t < t_single;
     t_single = lt ? t : t_single;
     n_single = lt ? node : n_single;
+  }
+  // hit = nearest root's node; container = the nearest node hit exactly once, else the hit node; adjacent = the other of
+  // the two nearest (:684-714)
+  __device__ __forceinline__ Nearest result() const {
+    Nearest r;
+    r.total = n_first < 0 ? 0 : (n_second < 0 ? 1 : 2);  // 0, 1, "2 or more"
+    r.t0 = t_first;
+    r.hit = n_first;
+    if (r.total <= 1) {
+      r.container = n_first;
+      r.adjacent = -1;
+    } else {
+      r.container = n_single >= 0 ? n_single : n_first;
+      r.adjacent = r.container == n_first ? n_second : n_first;
+    }
+    return r;
   }
 };
 
@@ -113,17 +144,13 @@ __device__ __forceinline__ Nearest nearest_surface(const SceneView& sv, const V3
       }
       double t_in, t_out;
       bool ok_in, ok_out;
-      box_roots(rec[kNodeParams], rec[kNodeParams + 1], rec[kNodeParams + 2], o, dl, inv, t_in, t_out, ok_in, ok_out);
-      best.add(t_in, node, ok_in);
-      best.add(t_out, node, ok_out);
-      best.add_single(t_out, node, ok_out && !ok_in);  // one root: it is the exit
+      box_roots(rec[kNodeHalf], rec[kNodeHalf + 1], rec[kNodeHalf + 2], o, dl, inv, t_in, t_out, ok_in, ok_out);
+      best.add_pair(t_in, t_out, node, ok_in, ok_out);
     } else if (gtype == 1) {
       double t1, t2;
       bool ok1, ok2;
       sphere_roots(rec[kNodeParams], o, dl, t1, t2, ok1, ok2);
-      best.add(t1, node, ok1);
-      best.add(t2, node, ok2);
-      best.add_single(t2, node, ok2 && !ok1);
+      best.add_pair(t1, t2, node, ok1, ok2);
     } else {
       const Roots r = cylinder_roots(rec[kNodeParams], rec[kNodeParams + 1], o, dl);
       int count = 0;
@@ -137,18 +164,24 @@ __device__ __forceinline__ Nearest nearest_surface(const SceneView& sv, const V3
       best.add_single(only, node, count == 1);
     }
   }
-  Nearest r;
-  r.total = best.n_first < 0 ? 0 : (best.n_second < 0 ? 1 : 2);  // 0, 1, "2 or more"
-  r.t0 = best.t_first;
-  r.hit = best.n_first;
-  if (r.total <= 1) {
-    r.container = best.n_first;
-    r.adjacent = -1;
-  } else {
-    r.container = best.n_single >= 0 ? best.n_single : best.n_first;
-    r.adjacent = r.container == best.n_first ? best.n_second : best.n_first;
+  return best.result();
+}
+
+// The same reduction for scenes made of axis-aligned boxes only (every LSC scene: world box, slab, coatings), chosen
+// per scene by the kernels' kBoxes instantiation: no primitive switch, no rotation, one reciprocal direction for all.
+__device__ __forceinline__ Nearest nearest_surface_boxes(const SceneView& sv, const V3& p, const V3& d) {
+  const int n_nodes = sv.hdr().n_nodes;
+  TwoNearest best;
+  const V3 inv = slab_reciprocal(d);
+  const double* rec = sv.node(0);
+  for (int node = 0; node < n_nodes; ++node, rec += kNodeWords) {
+    const V3 o = V3{p.x + rec[kNodeW2L + 3], p.y + rec[kNodeW2L + 7], p.z + rec[kNodeW2L + 11]};
+    double t_in, t_out;
+    bool ok_in, ok_out;
+    box_roots(rec[kNodeHalf], rec[kNodeHalf + 1], rec[kNodeHalf + 2], o, d, inv, t_in, t_out, ok_in, ok_out);
+    best.add_pair(t_in, t_out, node, ok_in, ok_out);
   }
-  return r;
+  return best.result();
 }
 
 // interpolate component c's absorption table at wavelength x
@@ -353,7 +386,7 @@ struct StepPlan {
 
 // First half of the reference's loop body (_kernel.pyx:654-760): budget check, intersect, kill check, free path.
 // Touches nothing but position, direction, wavelength and the step counter.
-template <bool kLog, class Rng, class P>
+template <bool kLog, bool kBoxes = false, class Rng, class P>
 __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
                                                    Rng& rng, LaneStats& st, StepPlan& plan) {
   const Header& H = sv.hdr();
@@ -367,7 +400,12 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
     return kDead;
   }
   ++st.steps;
-  const Nearest nh = nearest_surface(sv, ph.p, ph.d);
+  // Addressed streams draw the step's two uniforms (free path, surface test) BEFORE the intersection: the ten Philox
+  // rounds and the logarithm are chains that depend on nothing else, and issued here they overlap the slab arithmetic
+  // instead of following it (the kernel is bound by dependent-issue latency, not by issue slots: -3 % on config 2).
+  double ud_early = 0.0, u_early = 1.0;
+  if (Rng::kAddressed) rng.pair(kBlockPath, ud_early, u_early);
+  const Nearest nh = kBoxes ? nearest_surface_boxes(sv, ph.p, ph.d) : nearest_surface(sv, ph.p, ph.d);
   if (nh.total == 0) return kDead;  // :681-682
   plan.hit = nh.hit; plan.container = nh.container; plan.adjacent = nh.adjacent;
   plan.t = nh.t0;
@@ -382,7 +420,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
   if (alpha > kAlphaZero) {
     double ud;
     if (Rng::kAddressed) {
-      rng.pair(kBlockPath, ud, plan.u);
+      ud = ud_early; plan.u = u_early;
     } else {
       ud = rng.one(kBlockPath, 0);
     }
@@ -392,7 +430,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
       return kVolume;
     }
   } else if (Rng::kAddressed) {
-    plan.u = rng.one(kBlockPath, 1);
+    plan.u = u_early;
   }
   return kSurface;
 }
@@ -438,8 +476,15 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
   advance(ph, plan.t, sv.node(container)[kNodeSlowness]);
   const int c0 = sv.node_int(container, NI_COMP_START), cn = sv.node_int(container, NI_COMP_COUNT);
   double u_target, u_yield;
-  if (Rng::kAddressed) rng.pair(kBlockAbsorb, u_target, u_yield);
-  else u_target = rng.one(kBlockAbsorb, 0);
+  // addressed streams: all three blocks of the step up front, as independent chains (see classify_step)
+  double g1_early = 0.0, g2_early = 0.0, u_gamma_early = 0.0, u_delay_early = 0.0;
+  if (Rng::kAddressed) {
+    rng.pair(kBlockAbsorb, u_target, u_yield);
+    rng.pair(kBlockPhase, g1_early, g2_early);
+    rng.pair(kBlockEmit, u_gamma_early, u_delay_early);
+  } else {
+    u_target = rng.one(kBlockAbsorb, 0);
+  }
   const double target = u_target * plan.alpha;
   double running = 0.0;
   int comp = c0;
@@ -458,7 +503,8 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
   }
   if (radiative) {
     double g1, g2;
-    rng.pair(kBlockPhase, g1, g2);
+    if (Rng::kAddressed) { g1 = g1_early; g2 = g2_early; }
+    else rng.pair(kBlockPhase, g1, g2);
     ph.d = phase_direction(sv.comp_int(comp, CI_PHASE), cr[kCompPhaseParam], g1, g2);
     ph.source = comp;
     ++st.events;
@@ -473,7 +519,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
         p1 = interp_hinted(nm, ex, ec, en, cr[kCompEmsInvDx]);
       }
       double u_gamma, u_delay;
-      if (Rng::kAddressed) rng.pair(kBlockEmit, u_gamma, u_delay);
+      if (Rng::kAddressed) { u_gamma = u_gamma_early; u_delay = u_delay_early; }
       else u_gamma = rng.one(kBlockEmit, 0);
       const double gamma = p1 + (1.0 - p1) * u_gamma;
       ph.wl = interp(gamma, ec, ex, en);

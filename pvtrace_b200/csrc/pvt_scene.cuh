@@ -42,9 +42,10 @@ constexpr int kHeaderWords = sizeof(Header) / 8;
 static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
 
 // node record: w2l rows 0-2 (12) | l2w rows 0-2 (12) | params (4) | n (1) | ints: geom,surf | comp_start,comp_count |
-// facet_start,facet_count | n / c (seconds per cm) | ints: aligned (rotation part of w2l is exactly the identity), pad
+// facet_start,facet_count | n / c (seconds per cm) | ints: aligned (rotation part of w2l is exactly the identity), pad |
+// half (3): 0.5 * params, exact -- the box slabs sit at -half and +half | pad
 constexpr int kNodeW2L = 0, kNodeL2W = 12, kNodeParams = 24, kNodeIndex = 28, kNodeInts = 29, kNodeSlowness = 32,
-              kNodeWords = 34;
+              kNodeHalf = 34, kNodeWords = 38;
 // component record: qy, tau_rad, tau_nr, phase_param | ints: type,phase_type | abs_start,abs_n | ems_start,ems_n |
 // abs_inv_dx, ems_inv_dx (1/spacing of the x grid when it is uniform enough for interp_hinted, else 0) | pad
 constexpr int kCompQy = 0, kCompTauRad = 1, kCompTauNr = 2, kCompPhaseParam = 3, kCompInts = 4, kCompAbsInvDx = 7,
@@ -122,6 +123,7 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
     const bool aligned = m[0] == 1.0 && m[1] == 0.0 && m[2] == 0.0 && m[4] == 0.0 && m[5] == 1.0 && m[6] == 0.0 &&
                          m[8] == 0.0 && m[9] == 0.0 && m[10] == 1.0;
     put_ints(blob, iw + 4, aligned ? 1 : 0, 0);
+    for (int k = 0; k < 3; ++k) r[kNodeHalf + k] = 0.5 * S.geom_params[4 * i + k];
   }
   for (int c = 0; c < S.n_components; ++c) {
     double* r = &blob[h.off_comps + (size_t)c * kCompWords];

@@ -28,4 +28,8 @@ for rep in range(reps):
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
     d = ctx.read()
-    print(f"{name} n={n} rep={rep} {ms:.3f} ms {n / ms / 1e3:.1f} Mphot/s steps/photon {d['stats'][0] / n:.3f}", flush=True)
+    prof = d["stats"][4:8]
+    extra = ""
+    if prof.sum() > 0:  # library built with PVT_NVCC_FLAGS=-DPVT_PROFILE_STAGES: warp 0's cycles per stage, summed over CTAs
+        extra = "  stage1/bar1/stage2/bar2 % of warp-0 time: " + " ".join(f"{100 * v / prof.sum():.1f}" for v in prof)
+    print(f"{name} n={n} rep={rep} {ms:.3f} ms {n / ms / 1e3:.1f} Mphot/s steps/photon {d['stats'][0] / n:.3f}{extra}", flush=True)
