@@ -149,7 +149,7 @@ __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
   return 16 + (size_t)blob_words * 8 + pool_bytes(P);
 }
 
-// counters (u32): [0..3], [4..7] queue lengths, double buffered by iteration parity; then the cursors of the slice
+// counters (u32): [0..1], [4..5] queue lengths (VOLUME | SURFACE << 16, EXIT), double buffered by iteration parity; then the cursors of the slice
 enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrSteal = 12 /* [2]: stage 1, 2 */,
        kCtrAvail = 14 /* rays of the slice that have arrived (snapshot taken at the last barrier) */, kCtrCount = 16 };
 
@@ -213,15 +213,35 @@ __device__ __forceinline__ void store_slot(const PoolView& pool, int s, const Po
   if (kLog) pool.nlog[s] = ph.nlog;
 }
 
-// append slot `s` to queue `q` for the lanes where `pred` holds: one shared atomic per warp
-__device__ __forceinline__ void push_queue(uint16_t* q, uint32_t* counter, bool pred, int s, int lane) {
-  const unsigned m = __ballot_sync(kFullMask, pred);
-  if (m == 0) return;
-  uint32_t base = 0;
-  const int leader = __ffs(m) - 1;
-  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-  base = __shfl_sync(kFullMask, base, leader);
-  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)s;
+// Shared-memory atomics as single instructions.  (atomicAdd() by one elected lane makes the compiler wrap its own
+// warp aggregation -- vote, elect, popc, shuffle, a dozen one-lane instructions -- around every call.)
+__device__ __forceinline__ uint32_t atoms_add(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_addr(p)), "r"(v) : "memory");
+  return old;
+}
+
+// The VOLUME and SURFACE queue lengths share one 32-bit word (VOLUME | SURFACE << 16; the EXIT queue has its own), so
+// a classified chunk appends to the queues with one or two independent shared atomics.  (A 64-bit word for all three
+// would be a compare-and-swap loop: there is no native 64-bit shared-memory add.)
+__device__ __forceinline__ void push_queues(const uint16_t* qv_, const uint16_t* qs_, const uint16_t* qe_, uint32_t* lengths,
+                                            int cls, int s, int lane) {
+  uint16_t* qv = const_cast<uint16_t*>(qv_); uint16_t* qs = const_cast<uint16_t*>(qs_); uint16_t* qe = const_cast<uint16_t*>(qe_);
+  const unsigned mv = __ballot_sync(kFullMask, cls == kVolume), ms = __ballot_sync(kFullMask, cls == kSurface),
+                 me = __ballot_sync(kFullMask, cls == kExit || cls == kKill);
+  uint32_t base_vs = 0, base_e = 0;
+  if (lane == 0) {
+    if (mv | ms) base_vs = atoms_add(lengths, (uint32_t)__popc(mv) | ((uint32_t)__popc(ms) << 16));
+    if (me) base_e = atoms_add(lengths + 1, (uint32_t)__popc(me));
+  }
+  base_vs = __shfl_sync(kFullMask, base_vs, 0);
+  const unsigned below = (1u << lane) - 1u;
+  if (cls == kVolume) qv[(base_vs & 0xffffu) + __popc(mv & below)] = (uint16_t)s;
+  else if (cls == kSurface) qs[(base_vs >> 16) + __popc(ms & below)] = (uint16_t)s;
+  if (me) {
+    base_e = __shfl_sync(kFullMask, base_e, 0);
+    if (cls == kExit || cls == kKill) qe[base_e + __popc(me & below)] = (uint16_t)s;
+  }
 }
 
 // initial state of photon i of the bundle (global arrays or the emitter); out of line: the common path takes
@@ -239,7 +259,7 @@ __device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, l
 // take the next chunk of 32 work items of the current stage: one shared atomic per warp
 __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
   uint32_t c = 0;
-  if (lane == 0) c = atomicAdd(counter, 1u);
+  if (lane == 0) c = atoms_add(counter, 1u);
   return __shfl_sync(kFullMask, c, 0);
 }
 
@@ -273,12 +293,14 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
   uint32_t idle_iterations = 0;
 #ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
   long long prof[4] = {0, 0, 0, 0}, prof_t = clock64();
+  u64 prof_start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(prof_start));
 #define PVT_PROF(k) do { const long long now_ = clock64(); prof[k] += now_ - prof_t; prof_t = now_; } while (0)
 #else
 #define PVT_PROF(k) do { } while (0)
 #endif
   for (uint32_t iter = 0;; ++iter) {
-    uint32_t* qn = pool.counters + 4 * (iter & 1);
+    uint32_t* qn = pool.counters + 4 * (iter & 1);  // queue lengths of this iteration: VOLUME | SURFACE << 16, EXIT
     // ---------------- stage 1: refill + classify the pool, 32 slots per chunk; then produce fresh rays --------
     // Every warp takes chunks from one shared counter until the stage's work list is empty, so no warp has a
     // fixed share: classification chunks first (long), ray production chunks last (short).
@@ -336,8 +358,8 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
               // (another warp may see the inflated cursor meanwhile and take less than it could -- its slots
               // simply stay empty until the next iteration; indices below `avail` are handed out exactly once)
               const uint32_t cnt = (uint32_t)__popc(m);
-              base = atomicAdd(pool.counters + kCtrNext, cnt);
-              if (base + cnt > avail) atomicSub(pool.counters + kCtrNext, base + cnt - (base > avail ? base : avail));
+              base = atoms_add(pool.counters + kCtrNext, cnt);
+              if (base + cnt > avail) atoms_add(pool.counters + kCtrNext, 0u - (base + cnt - (base > avail ? base : avail)));
             }
             base = __shfl_sync(kFullMask, base, leader);
             const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
@@ -383,9 +405,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
               live = true;
             }
           }
-          push_queue(pool.qv, qn + 0, cls == kVolume, slot, lane);
-          push_queue(pool.qs, qn + 1, cls == kSurface, slot, lane);
-          push_queue(pool.qe, qn + 2, cls == kExit || cls == kKill, slot, lane);
+          push_queues(pool.qv, pool.qs, pool.qe, qn, cls, slot, lane);
         }
       }
     }
@@ -400,7 +420,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
 
     // ---------------- stage 2: interact; chunks of 32 entries of the VOLUME, SURFACE, EXIT queues in that
     // order (longest first), each chunk one kind of interaction with every lane busy ------------------------
-    const uint32_t cv = qn[0], cs = qn[1], ce = qn[2];
+    const uint32_t cv = qn[0] & 0xffffu, cs = qn[0] >> 16, ce = qn[1];
     const uint32_t nv = (cv + 31u) >> 5, ns = (cs + 31u) >> 5, ne = (ce + 31u) >> 5;
     if (tid < 4) pool.counters[4 * ((iter + 1) & 1) + tid] = 0u;
     if (tid == T - 1) {  // publish the cursors for the next iteration (nobody refills or produces in stage 2)
@@ -468,8 +488,19 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     PVT_PROF(3);
   }
 #ifdef PVT_PROFILE_STAGES
+#if PVT_PROFILE_STAGES == 2  // when CTAs finish: stats[4..7] = earliest start, earliest end, latest end, sum of ends (ns)
+  if (tid == 0) {
+    u64 now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    atomicMax(a.g_stats + 4, ~prof_start);  // minima as maxima of the complement (the slots start at zero)
+    atomicMax(a.g_stats + 5, ~now);
+    atomicMax(a.g_stats + 6, now);
+    atomicAdd(a.g_stats + 7, now - prof_start);
+  }
+#else
   if (tid == 0)
     for (int k = 0; k < 4; ++k) atomicAdd(a.g_stats + 4 + k, (u64)prof[k]);
+#endif
 #endif
   retire_cta(a, R, st);
 }

@@ -30,6 +30,11 @@ for rep in range(reps):
     d = ctx.read()
     prof = d["stats"][4:8]
     extra = ""
-    if prof.sum() > 0:  # library built with PVT_NVCC_FLAGS=-DPVT_PROFILE_STAGES: warp 0's cycles per stage, summed over CTAs
+    if int(prof[2]) > 10**15:  # -DPVT_PROFILE_STAGES=2: globaltimer stamps
+        M = (1 << 64) - 1
+        t0, e_min, e_max, dur_sum = ~int(prof[0]) & M, ~int(prof[1]) & M, int(prof[2]), int(prof[3])
+        ctas = 148
+        extra = f"  CTA ends: first {(e_min - t0) / 1e6:.3f} ms, last {(e_max - t0) / 1e6:.3f} ms, mean CTA duration {dur_sum / ctas / 1e6:.3f} ms"
+    elif prof.sum() > 0:  # library built with PVT_NVCC_FLAGS=-DPVT_PROFILE_STAGES: warp 0's cycles per stage, summed over CTAs
         extra = "  stage1/bar1/stage2/bar2 % of warp-0 time: " + " ".join(f"{100 * v / prof.sum():.1f}" for v in prof)
     print(f"{name} n={n} rep={rep} {ms:.3f} ms {n / ms / 1e3:.1f} Mphot/s steps/photon {d['stats'][0] / n:.3f}{extra}", flush=True)
