@@ -309,6 +309,7 @@ static int check_params(const pvt_params_t* P) {
 // CTAs of the wavefront kernel for a bundle of n rays, 0 when the bundle has to go through trace_kernel
 static int wave_grid(const pvt_context* c, const pvt_params_t* P) {
   if (c->wave_threads <= 0 || P->rng_mode != PVT_RNG_PHILOX || (P->flags & PVT_FLAG_REGISTER_KERNEL) || P->n <= 0) return 0;
+  if (P->n >= (1ll << 32) - 1024) return 0;  // the pool addresses photons of a bundle with 32 bits
   const long long want_blocks = (P->n + c->wave_pool - 1) / c->wave_pool;
   const long long resident = (long long)c->sm_count * c->wave_ctas;
   return (int)(want_blocks < resident ? want_blocks : resident);
@@ -350,11 +351,8 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
   a.slabs = c->slabs.ptr;
   int grid = wave_grid(c, P);
   a.arrived = arrived;
-  a.slice_pitch = 0;
   if (grid > 0) {
-    // persistent CTAs, each owning a contiguous slice of `slice_pitch` photons
-    a.slice_pitch = (P->n + grid - 1) / grid;
-    if (a.slice_pitch >= (1ll << 31)) return fail("bundle too large: at most 2^31 rays per resident CTA per call");
+    // persistent CTAs that claim blocks of photons from the work counter (zeroed above) as their pools drain
     PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
     PVT_TRY(launch_wave(c, &a, grid, st));
   } else {
@@ -519,7 +517,7 @@ struct Timer {
 
 constexpr int kMaxChunks = 64;           // pieces a host bundle is uploaded + traced in
 constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each (separate launches)
-constexpr size_t kStreamChunkRays = 320000;  // chunk of the streaming upload (one launch, arrival marks)
+constexpr size_t kStreamChunkRays = 1 << 16;  // smallest chunk of the streaming upload (one launch, arrival marks)
 
 // The streaming upload needs the copy stream to make progress WHILE the trace kernel runs.  Anything that
 // serialises the two (CUDA_LAUNCH_BLOCKING, a profiler replaying kernels one at a time) would leave the kernel
@@ -607,46 +605,57 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   if (!rc && z_pos) {
     rc = pvt_trace_device(c, z_pos, z_dir, z_wl, params, s_run);
   } else if (!rc && have_rays && n > 0 && wave_grid(c, params) > 0 && stream_upload_allowed()) {
-    // Streaming upload: the trace kernel starts at once and polls an arrival mark; the copy engine delivers, chunk
-    // by chunk, the next sub-block of EVERY CTA's slice (one strided 2-D copy per array) followed, in stream
-    // order, by the new mark.  Upload and trace overlap completely: total time ~ max(PCIe, kernel).
+    // Streaming upload: the trace kernel starts at once and polls an arrival mark; the copy engine delivers the
+    // arrays front to back in chunks (three plain copies each) followed, in stream order, by the new mark = rays
+    // complete so far.  CTAs claim photons in index order, so they consume the prefix as it lands.  Upload and trace
+    // overlap completely: total time ~ max(PCIe, kernel) + the trace of the LAST chunk -- hence chunks that start
+    // small (the kernel gets going at once), double up to a fifth of what is left (few, efficient copies) and
+    // shrink again towards the end (little left to trace when the last byte lands).
     streamed = true;
     static uint32_t* h_marks = nullptr;  // page-locked: the mark copies must not be staged
     if (!h_marks) PVT_CUDA(cudaHostAlloc((void**)&h_marks, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
     if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
     rc = g_rays.reserve(7 * n);
     double *d_pos = g_rays.ptr, *d_dir = g_rays.ptr + 3 * n, *d_wl = g_rays.ptr + 6 * n;
-    const long long grid = wave_grid(c, params), S = ((long long)n + grid - 1) / grid;
-    int chunks = (int)(n / kStreamChunkRays);
-    chunks = chunks < 1 ? 1 : (chunks > kMaxChunks ? kMaxChunks : chunks);
-    if (const char* env = getenv("PVT_UPLOAD_CHUNKS")) { const int v = atoi(env); if (v >= 1 && v <= kMaxChunks) chunks = v; }
-    const long long w = (S + chunks - 1) / chunks;
+    size_t min_chunk = kStreamChunkRays, shrink_div = 5;
+    if (const char* env = getenv("PVT_UPLOAD_MIN_CHUNK")) { const long v = atol(env); if (v >= 1024) min_chunk = (size_t)v; }
+    if (const char* env = getenv("PVT_UPLOAD_SHRINK")) { const int v = atoi(env); if (v >= 2 && v <= 64) shrink_div = (size_t)v; }
+    int chunks = 0;
     cudaError_t e = cudaSuccess;
+    static cudaEvent_t dbg[2] = {nullptr, nullptr};  // PVT_DEBUG_TIMING=1: how long the copy stream took
+    const bool dbg_on = getenv("PVT_DEBUG_TIMING") != nullptr;
+    if (dbg_on && !dbg[0]) { cudaEventCreate(&dbg[0]); cudaEventCreate(&dbg[1]); }
+    if (dbg_on) cudaEventRecord(dbg[0], s_copy);
     if (!rc) e = cudaMemsetAsync(c->arrived.ptr, 0, 4, s_copy);
     if (!rc && e == cudaSuccess) e = cudaEventRecord(s_uploaded[0], s_copy);
     if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(s_run, s_uploaded[0], 0);
     if (!rc && e == cudaSuccess) rc = trace_device_impl(c, d_pos, d_dir, d_wl, params, s_run, c->arrived.ptr);
-    for (int k = 0; k < chunks && !rc && e == cudaSuccess; ++k) {
-      const long long lo = (long long)k * w, wk = lo + w <= S ? w : S - lo;
-      if (wk <= 0) break;
-      // slices 0 .. full-1 hold at least lo + wk rays; slice `full` (the last non-empty one) may hold fewer
-      long long full = (long long)n >= lo + wk ? ((long long)n - (lo + wk)) / S + 1 : 0;
-      if (full > grid) full = grid;
-      if (full > 0) {
-        e = cudaMemcpy2DAsync(d_pos + 3 * lo, S * 24, positions + 3 * lo, S * 24, wk * 24, full, cudaMemcpyHostToDevice, s_copy);
-        if (e == cudaSuccess)
-          e = cudaMemcpy2DAsync(d_dir + 3 * lo, S * 24, directions + 3 * lo, S * 24, wk * 24, full, cudaMemcpyHostToDevice, s_copy);
-        if (e == cudaSuccess)
-          e = cudaMemcpy2DAsync(d_wl + lo, S * 8, wavelengths + lo, S * 8, wk * 8, full, cudaMemcpyHostToDevice, s_copy);
-      }
-      const long long tail_lo = full * S + lo, tail = (long long)n - tail_lo;  // partial row, < wk rays
-      if (e == cudaSuccess && full < grid && tail > 0 && tail < wk) {
-        e = cudaMemcpyAsync(d_pos + 3 * tail_lo, positions + 3 * tail_lo, tail * 24, cudaMemcpyHostToDevice, s_copy);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir + 3 * tail_lo, directions + 3 * tail_lo, tail * 24, cudaMemcpyHostToDevice, s_copy);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_wl + tail_lo, wavelengths + tail_lo, tail * 8, cudaMemcpyHostToDevice, s_copy);
-      }
-      h_marks[k] = (uint32_t)(lo + wk);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(c->arrived.ptr, h_marks + k, 4, cudaMemcpyHostToDevice, s_copy);
+    size_t lo = 0, grow = min_chunk;
+    while (lo < n && !rc && e == cudaSuccess) {
+      const size_t left = n - lo;
+      size_t m = left / shrink_div > min_chunk ? left / shrink_div : min_chunk;
+      if (m > grow) m = grow;
+      grow *= 2;
+      if (m > left || chunks == kMaxChunks - 1 || left - m < min_chunk / 2) m = left;
+      e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir + 3 * lo, directions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_wl + lo, wavelengths + lo, 8 * m, cudaMemcpyHostToDevice, s_copy);
+      lo += m;
+      h_marks[chunks] = (uint32_t)lo;
+      if (e == cudaSuccess) e = cudaMemcpyAsync(c->arrived.ptr, h_marks + chunks, 4, cudaMemcpyHostToDevice, s_copy);
+      ++chunks;
+    }
+    if (dbg_on) {
+      cudaEventRecord(dbg[1], s_copy);
+      cudaEventSynchronize(dbg[1]);
+      cudaStreamSynchronize(s_run);
+      float up = 0.f, t_start = 0.f;
+      cudaEventElapsedTime(&up, dbg[0], dbg[1]);
+      cudaEventElapsedTime(&t_start, t0, dbg[0]);
+      cudaEventRecord(t1, s_run); cudaEventSynchronize(t1);
+      float total = 0.f;
+      cudaEventElapsedTime(&total, t0, t1);
+      fprintf(stderr, "[pvt] upload started %.3f ms after t0, took %.3f ms (%d chunks); trace done at %.3f ms\n", t_start, up, chunks, total);
     }
     if (!rc && e != cudaSuccess) {
       // never leave the kernel polling: publish "everything arrived" so it drains, then report

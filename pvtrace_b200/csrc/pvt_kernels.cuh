@@ -38,12 +38,11 @@ struct TraceArgs {
   const double* blob;  // scene blob in global memory
   int blob_words;
   int scene_in_smem;   // 0: the blob did not fit into shared memory, read it through L1/L2 instead
-  // Streaming upload (wavefront kernel only): the kernel is launched BEFORE the host rays have arrived.  Photons
-  // are dealt to CTAs in contiguous slices of `slice_pitch`; the copy engine delivers the slices' next sub-blocks
-  // chunk by chunk and then stores, in stream order, how many rays of EVERY slice are complete into *arrived.
-  // A CTA never touches a ray at or beyond that mark.  arrived == nullptr: all rays are there.
+  // Streaming upload (wavefront kernel only): the kernel is launched BEFORE the host rays have arrived.  The copy
+  // engine delivers the arrays front to back, chunk by chunk, and after each chunk stores -- in stream order -- how
+  // many leading rays are complete into *arrived.  CTAs claim blocks of photons in index order from `work_counter`
+  // and never touch a ray at or beyond the mark.  arrived == nullptr: all rays are there.
   const uint32_t* arrived;
-  long long slice_pitch;
   const double* pos;   // [n,3] or null (=> emit on device)
   const double* dir;
   const double* wl;
@@ -149,9 +148,26 @@ __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
   return 16 + (size_t)blob_words * 8 + pool_bytes(P);
 }
 
-// counters (u32): [0..1], [4..5] queue lengths (VOLUME | SURFACE << 16, EXIT), double buffered by iteration parity; then the cursors of the slice
+// counters (u32): [0..1], [4..5] queue lengths (VOLUME | SURFACE << 16, EXIT), double buffered by iteration parity; then
+// the cursors of the CTA's ray SEQUENCE.  A CTA does not own a fixed share of the bundle: it claims blocks of kClaim
+// consecutive photons from a global counter as its pool drains (so all CTAs run dry together, whatever their
+// photons turned out to cost) and numbers the rays it has claimed 0, 1, 2, ...; block j of that sequence starts at
+// photon counters[kCtrBlock + (j & 3)].
+constexpr uint32_t kClaim = 512;
 enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrSteal = 12 /* [2]: stage 1, 2 */,
-       kCtrAvail = 14 /* rays of the slice that have arrived (snapshot taken at the last barrier) */, kCtrCount = 16 };
+       kCtrAvail = 14 /* sequence entries claimed AND arrived (snapshot taken at the last barrier) */,
+       kCtrClaimed = 15, kCtrExhausted = 16 /* the global counter has run past n */, kCtrBlock = 17 /* [4] */, kCtrCount = 21 };
+static_assert(kCtrCount <= 32, "the counters live in 128 bytes");
+
+// photon index (within the bundle) of entry q of the CTA's sequence
+__device__ __forceinline__ uint32_t sequence_photon(const uint32_t* counters, uint32_t q) {
+  return counters[kCtrBlock + ((q / kClaim) & 3u)] + (q % kClaim);
+}
+
+// One thread, between stages: claim another block when the look-ahead runs short, then advance `avail` over the
+// claimed entries whose photons have arrived.  `look_ahead` = ring size: production runs that far ahead of refills.
+__device__ __forceinline__ void extend_sequence(const TraceArgs& a, uint32_t* counters, uint32_t look_ahead);
+
 
 struct PoolView {
   double *px, *py, *pz, *dx, *dy, *dz, *wl, *trav, *dur, *t, *u, *alpha;
@@ -256,6 +272,40 @@ __device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, l
   }
 }
 
+__device__ __forceinline__ void extend_sequence(const TraceArgs& a, uint32_t* counters, uint32_t look_ahead) {
+  const uint32_t next = counters[kCtrNext];
+  uint32_t claimed = counters[kCtrClaimed];
+  // a new block J overwrites the table entry of block J - 4, whose entries must all have been handed out:
+  // claimed - next <= 3 kClaim.  (Refills happen in stage 1 only; this runs in stage 2.)
+  if (!counters[kCtrExhausted] && claimed - next < look_ahead + kClaim && claimed - next <= 3u * kClaim) {
+    const u64 b = atomicAdd(a.work_counter, (u64)kClaim);
+    if (b >= (u64)a.n) {
+      counters[kCtrExhausted] = 1u;
+    } else {
+      counters[kCtrBlock + ((claimed / kClaim) & 3u)] = (uint32_t)b;
+      const u64 left = (u64)a.n - b;
+      claimed += left < kClaim ? (uint32_t)left : kClaim;
+      if (left <= kClaim) counters[kCtrExhausted] = 1u;  // that was the last (possibly partial) block
+      counters[kCtrClaimed] = claimed;
+    }
+  }
+  uint32_t avail = counters[kCtrAvail];
+  if (!a.arrived) {
+    avail = claimed;
+  } else {
+    const uint32_t mark = *reinterpret_cast<const volatile uint32_t*>(a.arrived);
+    while (avail < claimed) {  // at most four blocks
+      const uint32_t b = counters[kCtrBlock + ((avail / kClaim) & 3u)], block_lo = avail - avail % kClaim;
+      const uint32_t block_n = claimed - block_lo < kClaim ? claimed - block_lo : kClaim;
+      const uint32_t there = mark > b ? (mark - b < block_n ? mark - b : block_n) : 0u;
+      if (block_lo + there <= avail) break;
+      avail = block_lo + there;
+      if (there < block_n) break;
+    }
+  }
+  counters[kCtrAvail] = avail;
+}
+
 // take the next chunk of 32 work items of the current stage: one shared atomic per warp
 __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
   uint32_t c = 0;
@@ -280,13 +330,12 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
   const LogColumns& L = a.log;
 
   const int tid = threadIdx.x, lane = tid & 31;
-  // contiguous slice of the photon range owned by this CTA
-  long long slice_lo = a.slice_pitch * (long long)blockIdx.x;
-  if (slice_lo > a.n) slice_lo = a.n;
-  const long long slice_hi = slice_lo + a.slice_pitch < a.n ? slice_lo + a.slice_pitch : a.n;
-  const uint32_t slice_n = (uint32_t)(slice_hi - slice_lo);
-  if (tid < kCtrCount) pool.counters[tid] = (tid == kCtrAvail && !a.arrived) ? slice_n : 0u;
+  if (tid < kCtrCount) pool.counters[tid] = 0u;
   for (int s = tid; s < P; s += T) pool.count[s] = -1;
+  __syncthreads();
+  if (tid == 0) {  // the first blocks of this CTA's sequence: enough to fill the pool
+    for (int k = 0; k < (P + (int)kClaim - 1) / (int)kClaim && k < 3; ++k) extend_sequence(a, pool.counters, (uint32_t)P);
+  }
   __syncthreads();
 
   LaneStats st;
@@ -329,7 +378,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         if (chunk < ray_chunks) {
           const uint32_t o = lo + chunk * 32u + (uint32_t)lane;  // slice offset of this lane's ray
           if (o < hi) {
-            const long long i = slice_lo + o;
+            const long long i = sequence_photon(pool.counters, o);
             double* r = pool.ring + (o & (K - 1));
             if (a.pos) {
               // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles);
@@ -364,7 +413,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
             base = __shfl_sync(kFullMask, base, leader);
             const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
             if (dead && mine < avail) {
-              const long long i = slice_lo + mine;
+              const long long i = sequence_photon(pool.counters, mine);
               if (mine < ring_hi) {
                 const double* r = pool.ring + (mine & (K - 1));
                 ph.p = V3{r[0], r[K], r[2 * K]};
@@ -380,7 +429,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
               ph.log_ray = (kLog && a.record_every > 0) ? sampled_ordinal(i, a.record_every) : -1;
               ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
               begin_photon<kLog>(ph, L, sp, st);
-              pool.idx[slot] = mine;
+              pool.idx[slot] = (uint32_t)i;
               if (kLog) pool.log_ray[slot] = ph.log_ray;
               pool.seen[slot] = 0ull;
               fresh = true;
@@ -390,7 +439,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
           if (fresh || !dead) {
             if (!fresh) load_slot_head<kLog>(pool, slot, ph, sp.max_events);
             PhiloxStream rng;
-            rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
+            rng.id = id0 + (u64)pool.idx[slot];
             StepPlan plan;
             cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan);
             if (cls == kDead) {
@@ -411,7 +460,8 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     }
     // leave when no slot is live and every ray of the slice has been taken; while rays are still in flight from
     // the host the CTA keeps polling (bounded: a transfer that never completes must not hang the device)
-    const bool pending = pool.counters[kCtrNextSnap] < slice_n && idle_iterations < kMaxIdleIterations;
+    const bool pending = !(pool.counters[kCtrExhausted] && pool.counters[kCtrNextSnap] >= pool.counters[kCtrClaimed]) &&
+                         idle_iterations < kMaxIdleIterations;
     PVT_PROF(0);
     const bool any_live = __syncthreads_count(live) > 0;
     PVT_PROF(1);
@@ -426,10 +476,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     if (tid == T - 1) {  // publish the cursors for the next iteration (nobody refills or produces in stage 2)
       pool.counters[kCtrRingHi] = pool.counters[kCtrRingHiPending];
       pool.counters[kCtrNextSnap] = pool.counters[kCtrNext];
-      if (a.arrived) {
-        const uint32_t mark = *reinterpret_cast<const volatile uint32_t*>(a.arrived);
-        pool.counters[kCtrAvail] = mark < slice_n ? mark : slice_n;
-      }
+      extend_sequence(a, pool.counters, (uint32_t)K);
       pool.counters[kCtrSteal] = 0u;  // stage 1's work counter
     }
     for (;;) {
@@ -453,7 +500,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         PoolPhoton ph;
         load_slot<kLog>(pool, slot, ph, sp.max_events);
         PhiloxStream rng;
-        rng.id = id0 + (u64)(slice_lo + pool.idx[slot]);
+        rng.id = id0 + (u64)pool.idx[slot];
         rng.begin_step((uint32_t)ph.count);
         StepPlan plan;
         plan.t = pool.t[slot]; plan.u = pool.u[slot]; plan.alpha = pool.alpha[slot];

@@ -1,0 +1,24 @@
+import os, sys, time
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import pvtrace_b200 as pv
+from pvtrace_b200.device import configs
+from pvtrace_b200.engine import _cuda
+n = 10_000_000
+scene = configs.lsc_default()
+compiled, emitter = pv.engine.compile_scene(scene), pv.engine.compile_emitter(scene)
+h = [torch.empty((n, 3), dtype=torch.float64).pin_memory(), torch.empty((n, 3), dtype=torch.float64).pin_memory(),
+     torch.empty(n, dtype=torch.float64).pin_memory()]
+d = [torch.empty_like(t, device="cuda") for t in h]
+ctx = _cuda.Context(compiled, emitter, 0)
+ctx.emit(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), n, seed=1)
+for a, b in zip(h, d): a.copy_(b)
+torch.cuda.synchronize()
+arrs = [t.numpy() for t in h]
+for chunks in (8, 16, 32, 48):
+    os.environ["PVT_UPLOAD_CHUNKS"] = str(chunks)
+    for rep in range(3):
+        t0 = time.perf_counter()
+        out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
+        dt = time.perf_counter() - t0
+    print(f"chunks={chunks:2d}: wall {dt*1e3:.2f} ms  device-elapsed {el*1e3:.2f} ms", flush=True)
