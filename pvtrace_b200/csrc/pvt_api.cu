@@ -49,6 +49,8 @@ struct pvt_context {
   DeviceBuffer<double> packed;
   DeviceBuffer<uint32_t> arrived;  // streaming-upload mark (see TraceArgs::arrived)
   DeviceBuffer<u64> slabs;  // CTA-private tally slabs of one launch: [max_grid][10 R]
+  DeviceBuffer<double> requests;  // tally-request rings of the service-warp kernels: [resident CTAs][kReqWords][pool]
+  int wave_service = 0;     // service threads per CTA (0: tallies are made in place)
   int max_grid = 0;
   int wave_threads = 0;     // CTA size of the wavefront kernel for this scene, 0: scene needs trace_kernel
   int wave_pool = 0;        // photon slots per CTA
@@ -139,9 +141,27 @@ static int wave_attr(K kernel, size_t smem) {
       PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, false>, c->wave_smem));                 \
       PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, true>, c->wave_smem));                  \
       PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, false>, c->wave_smem));                  \
+      if (T == 512 && P == 1024 && B == 1) {                                                     \
+        constexpr int TS = (T == 512 && P == 1024 && B == 1) ? 128 : 0;                          \
+        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, false, TS>, c->wave_smem));           \
+        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, true, TS>, c->wave_smem));            \
+        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, false, TS>, c->wave_smem));            \
+        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, true, TS>, c->wave_smem));             \
+      }                                                                                          \
       return wave_attr(wavefront_kernel<T, P, B, true, true>, c->wave_smem);                     \
     }                                                                                            \
     const bool log = args->record_every > 0;                                                     \
+    if (T == 512 && P == 1024 && B == 1 && c->wave_service > 0) {                                \
+      constexpr int TS = (T == 512 && P == 1024 && B == 1) ? 128 : 0;                            \
+      if (c->wave_boxes) {                                                                       \
+        if (log) wavefront_kernel<T, P, B, true, true, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);    \
+        else wavefront_kernel<T, P, B, false, true, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);       \
+      } else {                                                                                   \
+        if (log) wavefront_kernel<T, P, B, true, false, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);   \
+        else wavefront_kernel<T, P, B, false, false, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);      \
+      }                                                                                          \
+      return 0;                                                                                  \
+    }                                                                                            \
     if (c->wave_boxes) {                                                                         \
       if (log) wavefront_kernel<T, P, B, true, true><<<grid, T, c->wave_smem, st>>>(*args);      \
       else wavefront_kernel<T, P, B, false, true><<<grid, T, c->wave_smem, st>>>(*args);         \
@@ -217,6 +237,9 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   c->max_grid = c->sm_count * 8;
   if (!rc) rc = c->slabs.reserve((size_t)c->max_grid * 10 * c->R() + 1);
   if (!rc) rc = c->arrived.reserve(4);
+  c->wave_service = (c->wave_threads == 512 && c->wave_pool == 1024 && c->wave_ctas == 1 && c->R() > 0 &&
+                     !(getenv("PVT_TALLY_IN_PLACE") && atoi(getenv("PVT_TALLY_IN_PLACE")))) ? 128 : 0;
+  if (!rc && c->wave_service) rc = c->requests.reserve((size_t)c->sm_count * c->wave_ctas * 2 * kReqWords * c->wave_pool);
   if (!rc && cudaMemcpy(c->blob.ptr, c->host_blob.data(), (size_t)c->blob_words * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     rc = fail("scene upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (!rc && cudaMemset(c->tallies.ptr, 0, c->tally_words * 8) != cudaSuccess)
@@ -349,6 +372,7 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
                      c->travelled.ptr, c->duration.ptr};
 
   a.slabs = c->slabs.ptr;
+  a.requests = c->requests.ptr;
   int grid = wave_grid(c, P);
   a.arrived = arrived;
   if (grid > 0) {

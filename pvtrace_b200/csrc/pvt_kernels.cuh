@@ -51,6 +51,7 @@ struct TraceArgs {
   StepParams sp;
   u64* work_counter;
   u64* slabs;       // [gridDim.x][10 R] CTA-private tally slabs, zero on entry
+  double* requests; // [gridDim.x][kReqWords][pool slots] tally requests of one iteration (service-warp kernels)
   u64* g_distinct;  // [R]
   u64* g_cross;     // [R]
   double* g_sums;   // [R,8]
@@ -141,8 +142,8 @@ __host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 115
 // Shared memory left over is L1: the kernel is sensitive to it (24 KB more of shared memory cost 5 %), so the pool
 // carries nothing it does not need.
 __host__ __device__ constexpr size_t pool_bytes(int P) {
-  return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/) + (size_t)ring_size(P) * 7 * 8 +
-         128 /*counters*/;
+  return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/ + 1 /*tallied*/) +
+         (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/;
 }
 __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
   return 16 + (size_t)blob_words * 8 + pool_bytes(P);
@@ -156,7 +157,10 @@ __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
 constexpr uint32_t kClaim = 512;
 enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, kCtrSteal = 12 /* [2]: stage 1, 2 */,
        kCtrAvail = 14 /* sequence entries claimed AND arrived (snapshot taken at the last barrier) */,
-       kCtrClaimed = 15, kCtrExhausted = 16 /* the global counter has run past n */, kCtrBlock = 17 /* [4] */, kCtrCount = 21 };
+       kCtrClaimed = 15, kCtrExhausted = 16 /* the global counter has run past n */, kCtrBlock = 17 /* [4] */,
+       // service warps (tally requests): batch id published, requests in it, chunk cursor, chunks done, warps that
+       // have left the batch, exit flag
+       kSvcBatch = 21, kSvcCount = 22, kSvcSteal = 23, kSvcDone = 24, kSvcAck = 25, kSvcExit = 26, kCtrCount = 27 };
 static_assert(kCtrCount <= 32, "the counters live in 128 bytes");
 
 // photon index (within the bundle) of entry q of the CTA's sequence
@@ -175,6 +179,7 @@ struct PoolView {
   int32_t *count, *source, *nlog, *log_ray;
   uint32_t *idx, *ids;
   uint16_t *qv, *qs, *qe;
+  uint8_t* tallied;    // service-warp kernels: this photon has sent a tally request before (its seen mask is live)
   double* ring;        // [7][K]: px py pz dx dy dz wl of photons [ring_lo, ring_hi) of the slice, at offset mod K
   uint32_t* counters;
 };
@@ -192,7 +197,8 @@ __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
   v.log_ray = w + 5 * P;
   uint16_t* h = reinterpret_cast<uint16_t*>(w + 6 * P);
   v.qv = h; v.qs = h + P; v.qe = h + 2 * P;
-  v.counters = reinterpret_cast<uint32_t*>(h + 3 * P);  // P is a multiple of 32: 4-byte aligned
+  v.tallied = reinterpret_cast<uint8_t*>(h + 3 * P);
+  v.counters = reinterpret_cast<uint32_t*>(v.tallied + P);  // P is a multiple of 32: 4-byte aligned
   return v;
 }
 
@@ -213,11 +219,11 @@ __device__ __forceinline__ void load_slot_head(const PoolView& pool, int s, Pool
     ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * max_events;
   }
 }
-template <bool kLog>
+template <bool kLog, bool kSeen = true>
 __device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, int max_events) {
   load_slot_head<kLog>(pool, s, ph, max_events);
   ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; ph.source = pool.source[s];
-  const u64 seen = pool.seen[s];
+  const u64 seen = kSeen ? pool.seen[s] : 0ull;  // (the service warps own the masks when there are any)
   ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
 }
 template <bool kLog>
@@ -313,9 +319,91 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
   return __shfl_sync(kFullMask, c, 0);
 }
 
-// T threads per CTA, P pool slots (multiple of 32, typically ~2T), B resident CTAs per SM
-template <int T, int P, int B, bool kLog, bool kBoxes = false>
-__global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__ TraceArgs a) {
+// ---- service warps --------------------------------------------------------------------------------------------
+// Tallying in place costs a stage-2 chunk a third of its latency for the few lanes that have something to tally.
+// Kernels instantiated with S > 0 run S extra threads (one warpgroup) that do nothing else: stage 2 only WRITES a
+// request (64 bytes: wavelength, duration, travelled, cosine, local point, packed ids) into a per-CTA ring in global
+// memory (L2, two halves by iteration parity); the barrier that ends the stage makes the batch visible, thread 0
+// publishes it at the top of the next iteration, and the service warps tally it 32 requests at a time while the
+// tracing warps go on.  They have a whole iteration to do so (the half is rewritten two stages later), so nobody
+// waits for anybody in the steady state.  The distinct-ray (`seen`) masks are theirs alone: a request only says
+// whether it is the photon's first, batches are served in order and a slot appears once per batch.  The tracing
+// warps synchronise among themselves on a named barrier, and the registers of the CTA are re-divided between the
+// two roles (setmaxnreg).
+constexpr int kReqWords = 8;
+constexpr int kSvcWarps = 4;
+constexpr int kTracerRegs = 104, kSvcRegs = 64;  // 512 x 104 + 128 x 64 = 640 x 96, what the CTA is launched with (the pool is per CTA)
+
+template <int T, int S>
+__device__ __forceinline__ void sync_tracers() {
+  if (S == 0) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(T) : "memory");
+}
+template <int T, int S>
+__device__ __forceinline__ int sync_tracers_count(bool pred) {
+  if (S == 0) return __syncthreads_count(pred);
+  int total;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.popc.u32 %0, 1, %2, q;\n\t}"
+               : "=r"(total) : "r"((int)pred), "n"(T) : "memory");
+  return total;
+}
+__device__ __forceinline__ uint32_t peek(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// what stage 2 leaves for the service warps
+__device__ __forceinline__ void write_request(double* ring, int stride, uint32_t at, const PoolPhoton& ph, const TallyReq& tr,
+                                              int slot, bool fresh) {
+  double* q = ring + at;
+  const u64 packed = (u64)(uint32_t)tr.sel | ((u64)(uint32_t)tr.node << 8) | ((u64)(uint32_t)(tr.face + 1) << 16) |
+                     ((u64)(tr.has_normal ? 1u : 0u) << 20) | ((u64)(fresh ? 1u : 0u) << 21) | ((u64)(uint32_t)slot << 32);
+  q[0] = ph.wl; q[stride] = ph.duration; q[2 * stride] = ph.travelled; q[3 * stride] = tr.cosine;
+  q[4 * stride] = tr.lp.x; q[5 * stride] = tr.lp.y; q[6 * stride] = tr.lp.z;
+  q[7 * stride] = __longlong_as_double((long long)packed);
+}
+
+template <int P>
+__device__ __forceinline__ void service_loop(const SceneView& sv, const TallySink& sink, const PoolView& pool,
+                                             const double* ring, int lane) {
+  for (;;) {
+    // sleep on named barrier 2 until warp 0 of the tracers arrives with a batch (or with the exit flag): no polling
+    asm volatile("bar.sync 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
+    if (peek(pool.counters + kSvcExit)) return;
+    const uint32_t batch = peek(pool.counters + kSvcBatch);
+    const uint32_t count = peek(pool.counters + kSvcCount), chunks = (count + 31u) >> 5;
+    const double* half = ring + (size_t)((batch - 1u) & 1u) * kReqWords * P;  // batch b was written in iteration b - 1
+    for (;;) {
+      const uint32_t chunk = steal_chunk(pool.counters + kSvcSteal, lane);
+      if (chunk >= chunks) break;
+      const uint32_t at = chunk * 32u + (uint32_t)lane;
+      if (at < count) {
+        const double* q = half + at;
+        const double wl = __ldcg(q), duration = __ldcg(q + P), travelled = __ldcg(q + 2 * P), cosine = __ldcg(q + 3 * P);
+        const V3 lp = V3{__ldcg(q + 4 * P), __ldcg(q + 5 * P), __ldcg(q + 6 * P)};
+        const u64 packed = (u64)__double_as_longlong(__ldcg(q + 7 * P));
+        const int sel = (int)(packed & 0xffu), node = (int)((packed >> 8) & 0xffu), face = (int)((packed >> 16) & 0xfu) - 1;
+        const bool has_normal = (packed >> 20) & 1u, fresh = (packed >> 21) & 1u;
+        const int slot = (int)(packed >> 32);
+        // the seen masks belong to the service warps: batches are served in order and a slot appears once per batch
+        const u64 seen_bits = fresh ? 0ull : pool.seen[slot];
+        V3 nw = V3{0.0, 0.0, 0.0};
+        if (has_normal && face < 0) {  // not a box face: the facet test needs the world normal, recomputed from the point
+          const double* rec = sv.node(node);
+          nw = map_vector(rec + kNodeL2W, outward_normal(sv.node_int(node, NI_GEOM), rec + kNodeParams, lp));
+        }
+        SeenMask<2> seen;
+        seen.w[0] = (uint32_t)seen_bits; seen.w[1] = (uint32_t)(seen_bits >> 32);
+        seen = tally_event<2>(sv, sink, seen, sel, node, face, has_normal, nw, lp, cosine, wl, duration, travelled);
+        pool.seen[slot] = (u64)seen.w[0] | ((u64)seen.w[1] << 32);
+      }
+      __syncwarp();
+    }
+    __threadfence_block();
+    if (lane == 0) atoms_add(pool.counters + kSvcAck, 1u);
+  }
+}
+
+// T tracing threads per CTA, P pool slots (multiple of 32, typically ~2T), B resident CTAs per SM, S service threads
+template <int T, int P, int B, bool kLog, bool kBoxes = false, int S = 0>
+__global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int K = ring_size(P);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -330,8 +418,8 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
   const LogColumns& L = a.log;
 
   const int tid = threadIdx.x, lane = tid & 31;
-  if (tid < kCtrCount) pool.counters[tid] = 0u;
-  for (int s = tid; s < P; s += T) pool.count[s] = -1;
+  if (tid < kCtrCount) pool.counters[tid] = tid == kSvcAck ? (uint32_t)kSvcWarps : 0u;
+  for (int s = tid; s < P; s += T + S) pool.count[s] = -1;
   __syncthreads();
   if (tid == 0) {  // the first blocks of this CTA's sequence: enough to fill the pool
     for (int k = 0; k < (P + (int)kClaim - 1) / (int)kClaim && k < 3; ++k) extend_sequence(a, pool.counters, (uint32_t)P);
@@ -339,6 +427,15 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
   __syncthreads();
 
   LaneStats st;
+  double* const ring = S > 0 ? a.requests + (size_t)blockIdx.x * 2 * kReqWords * P : nullptr;  // two halves, by parity
+  if (S > 0 && tid >= T) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
+    service_loop<P>(sv, sink, pool, ring, lane);
+    __threadfence();
+    retire_cta(a, R, st);
+    return;
+  }
+  if (S > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTracerRegs));
   uint32_t idle_iterations = 0;
 #ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
   long long prof[4] = {0, 0, 0, 0}, prof_t = clock64();
@@ -354,6 +451,22 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     // Every warp takes chunks from one shared counter until the stage's work list is empty, so no warp has a
     // fixed share: classification chunks first (long), ray production chunks last (short).
     bool live = false;
+    if (S > 0 && iter > 0 && tid < 32) {
+      // Warp 0 publishes the requests written by the stage 2 that just ended (its barrier made them visible) and
+      // wakes the service warps.  Batch b is written in stage 2 of iteration b - 1 into ring half (b - 1) & 1 and
+      // served during iteration b -- a whole iteration of slack -- so the wait for the PREVIOUS batch's
+      // acknowledgements almost never spins.
+      if (tid == 0) {
+        while (peek(pool.counters + kSvcAck) < (uint32_t)kSvcWarps) { }
+        pool.counters[kSvcAck] = 0u;
+        pool.counters[kSvcCount] = pool.counters[4 * ((iter + 1) & 1) + 2];
+        pool.counters[kSvcSteal] = 0u;
+        pool.counters[kSvcBatch] = iter;
+        __threadfence_block();
+      }
+      __syncwarp();
+      asm volatile("bar.arrive 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
+    }
     {
       const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
       // rays to produce: [max(ring_hi, next), next + K), `next` being the snapshot taken at the last barrier, so
@@ -431,7 +544,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
               begin_photon<kLog>(ph, L, sp, st);
               pool.idx[slot] = (uint32_t)i;
               if (kLog) pool.log_ray[slot] = ph.log_ray;
-              pool.seen[slot] = 0ull;
+              if (S > 0) pool.tallied[slot] = 0; else pool.seen[slot] = 0ull;
               fresh = true;
             }
           }
@@ -463,7 +576,7 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
     const bool pending = !(pool.counters[kCtrExhausted] && pool.counters[kCtrNextSnap] >= pool.counters[kCtrClaimed]) &&
                          idle_iterations < kMaxIdleIterations;
     PVT_PROF(0);
-    const bool any_live = __syncthreads_count(live) > 0;
+    const bool any_live = sync_tracers_count<T, S>(live) > 0;
     PVT_PROF(1);
     if (!any_live && !pending) break;
     idle_iterations = any_live ? 0u : idle_iterations + 1u;
@@ -498,7 +611,9 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
       }
       if (slot >= 0) {
         PoolPhoton ph;
-        load_slot<kLog>(pool, slot, ph, sp.max_events);
+        TallyReq tr;
+        bool alive = false;
+        load_slot<kLog, S == 0>(pool, slot, ph, sp.max_events);
         PhiloxStream rng;
         rng.id = id0 + (u64)pool.idx[slot];
         rng.begin_step((uint32_t)ph.count);
@@ -507,8 +622,6 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
         const uint32_t ids = pool.ids[slot];
         plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
         if (plan.adjacent == 0xff) plan.adjacent = -1;
-        bool alive = false;
-        TallyReq tr;
         if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
         else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
         else if (ids >> 24) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
@@ -519,20 +632,33 @@ __global__ void __launch_bounds__(T, B) wavefront_kernel(const __grid_constant__
           if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
           pool.count[slot] = -1;
         }
-        // Tallied in place, by the few lanes of the chunk that have something to tally (~5 active lanes; a quarter
-        // of the kernel's issue slots).  Queueing these requests to serve them 32 at a time in the next stage 1 cut
-        // the instruction count by 8 % but was SLOWER every time it was tried (10.7 -> 11.7, 9.1 -> 11.1 ms on config
-        // 2): the extra short chunks break the two-rounds-per-warp balance of the stage (barrier stalls 9 % -> 23 %)
-        // and the queue's shared memory comes out of L1.
-        if (tr.sel >= 0) {
+        // Tallied in place (S == 0), by the few lanes of the chunk that have something to tally (~8 active lanes, a
+        // fifth of the kernel's issue slots and a third of this stage's latency) -- or handed to the service warps.
+        if (S == 0 && tr.sel >= 0) {
           tally(sv, sink, ph, tr);
           if (alive) pool.seen[slot] = (u64)ph.seen[0] | ((u64)ph.seen[1] << 32);
+        }
+        if (S > 0 && tr.sel >= 0) {
+          // every requesting lane reserves its own ring entry (one shared atomic instruction for the warp, no
+          // reconvergence needed) while the values are still in registers
+          const uint32_t at = atoms_add(qn + 2, 1u);
+          write_request(ring + (size_t)(iter & 1u) * kReqWords * P, P, at, ph, tr, slot, pool.tallied[slot] == 0);
+          pool.tallied[slot] = 1;
         }
       }
     }
     PVT_PROF(2);
-    __syncthreads();
+    sync_tracers<T, S>();
     PVT_PROF(3);
+  }
+  if (S > 0 && tid < 32) {  // the last batch was published at the top of the final iteration
+    if (tid == 0) {
+      while (peek(pool.counters + kSvcAck) < (uint32_t)kSvcWarps) { }
+      pool.counters[kSvcExit] = 1u;
+      __threadfence_block();
+    }
+    __syncwarp();
+    asm volatile("bar.arrive 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
   }
 #ifdef PVT_PROFILE_STAGES
 #if PVT_PROFILE_STAGES == 2  // when CTAs finish: stats[4..7] = earliest start, earliest end, latest end, sum of ends (ns)
