@@ -250,9 +250,12 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 8>, c->smem_bytes, &c->blocks_per_sm[3]);
   if (!rc && c->wave_threads > 0) rc = launch_wave(c, nullptr, 0, 0);  // attribute setup only
   if (!rc && c->smem_bytes > 48 * 1024 &&
-      (cudaFuncSetAttribute(intersect_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess))
+      (cudaFuncSetAttribute(intersect_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
+       cudaFuncSetAttribute(intersect_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
+       cudaFuncSetAttribute(intersect_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
+       cudaFuncSetAttribute(intersect_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
+       cudaFuncSetAttribute(intersect_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
+       cudaFuncSetAttribute(intersect_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess))
     rc = fail("cudaFuncSetAttribute(intersect_kernel) failed");
   if (rc) {
     pvt_context_destroy(c);
@@ -501,14 +504,20 @@ extern "C" int pvt_intersect_device(pvt_context_t* c, const double* d_pos, const
   if (!c) return fail("ctx is NULL");
   if (n <= 0) return 0;
   PVT_CUDA(cudaSetDevice(c->device));
-  int ctas = 2;  // 120 registers, no spills: measured best (2.71 TB/s of 68 B/ray traffic on config 2)
+  int ctas = 3;  // 80 registers with one tile in flight: measured best (4.26 TB/s of 68 B/ray traffic on config 2)
   if (const char* env = getenv("PVT_INTERSECT_CTAS")) ctas = atoi(env);
-#define PVT_INTERSECT_LAUNCH(K)                                                                                      \
-  intersect_kernel<K><<<intersect_grid(c, n, intersect_kernel<K>), 256, c->smem_bytes, (cudaStream_t)stream>>>(      \
+#define PVT_INTERSECT_LAUNCH(K, BX)                                                                                  \
+  intersect_kernel<K, BX><<<intersect_grid(c, n, intersect_kernel<K, BX>), 256, c->smem_bytes, (cudaStream_t)stream>>>( \
       c->hdr, c->blob.ptr, c->blob_words, c->scene_in_smem, d_pos, d_dir, n, d_t0, d_hit, d_container, d_adjacent)
-  if (ctas <= 2) PVT_INTERSECT_LAUNCH(2);
-  else if (ctas == 3) PVT_INTERSECT_LAUNCH(3);
-  else PVT_INTERSECT_LAUNCH(4);
+  if (c->wave_boxes) {
+    if (ctas <= 2) PVT_INTERSECT_LAUNCH(2, true);
+    else if (ctas == 3) PVT_INTERSECT_LAUNCH(3, true);
+    else PVT_INTERSECT_LAUNCH(4, true);
+  } else {
+    if (ctas <= 2) PVT_INTERSECT_LAUNCH(2, false);
+    else if (ctas == 3) PVT_INTERSECT_LAUNCH(3, false);
+    else PVT_INTERSECT_LAUNCH(4, false);
+  }
   PVT_CUDA(cudaGetLastError());
   return 0;
 }
