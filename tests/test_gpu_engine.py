@@ -360,3 +360,29 @@ def test_stream_from_worker_thread_is_additive(gpu):
     assert traced == 30000
     for key in total:
         assert (total[key] == whole[key]).all(), key
+
+
+@pytest.mark.parametrize("name", ["lsc", "mixed"])
+def test_service_warps_in_place_tallies_and_register_kernel_agree(gpu, monkeypatch, name):
+    """The three ways a tally can be made -- by the service warps from a request (default), in place by the tracing
+    warps (PVT_TALLY_IN_PLACE=1) and by the one-photon-per-lane kernel -- see the same events: integer fields are
+    identical, moment sums agree to summation order.  Bundle sizes straddle the 512-photon claim blocks and the
+    1024-slot pool (one short block, one photon more than two blocks, a ragged tail over many CTAs)."""
+    scene = scenes.SCENES[name]()
+    compiled, emitter = pv.engine.compile_scene(scene), pv.engine.compile_emitter(scene)
+    for n in (1, 511, 1025, 70001):
+        results = {}
+        for mode in ("service", "in_place", "register"):
+            monkeypatch.setenv("PVT_TALLY_IN_PLACE", "1" if mode == "in_place" else "0")
+            with _cuda.Context(compiled, emitter, 0) as ctx:
+                ctx.reset()
+                ctx.trace(n, 21, record_every=0, flags=_cuda.FLAG_REGISTER_KERNEL if mode == "register" else 0)
+                results[mode] = ctx.read()
+        base = results["service"]
+        assert base["stats"][_cuda.STAT_RAYS] == n
+        for mode in ("in_place", "register"):
+            other = results[mode]
+            assert other["stats"][_cuda.STAT_RAYS] == n and other["stats"][_cuda.STAT_STEPS] == base["stats"][_cuda.STAT_STEPS]
+            for key in ("rec_distinct", "rec_crossings", "rec_bins"):
+                assert (base[key] == other[key]).all(), (n, mode, key)
+            np.testing.assert_allclose(base["rec_sums"], other["rec_sums"], rtol=1e-10, atol=1e-300)
