@@ -441,7 +441,7 @@ __device__ __forceinline__ void kill_step(const SceneView& sv, const LogColumns&
                                           LaneStats& st, const StepPlan& plan, TallyReq& tr) {
   ++st.events;
   PVT_LOG(ph, PVT_EV_KILL, -1, plan.container, -1, -1);
-  if (sv.hdr().n_recorders > 0) {
+  if (sv.hdr().n_recorders > 0 && sv.has_recorders(plan.container, PVT_REC_KILLED)) {
     tr.sel = PVT_REC_KILLED; tr.node = plan.container; tr.has_normal = false; tr.normal = V3{0.0, 0.0, 0.0};
     tr.lp = map_point(sv.node(plan.container) + kNodeW2L, ph.p); tr.cosine = 1.0;
   }
@@ -455,7 +455,7 @@ __device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns&
   advance(ph, plan.t, sv.node(plan.container)[kNodeSlowness]);
   ++st.events;
   PVT_LOG(ph, PVT_EV_EXIT, hit, plan.container, plan.adjacent, -1);
-  if (sv.hdr().n_recorders > 0) {
+  if (sv.hdr().n_recorders > 0 && sv.has_recorders(hit, PVT_REC_EXIT)) {
     const double* rec = sv.node(hit);
     const V3 lp = map_point(rec + kNodeW2L, ph.p);
     int face;
@@ -543,7 +543,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
     PVT_LOG(ph, PVT_EV_NONRADIATIVE, -1, container, -1, comp);
     sel = PVT_REC_LOST;
   }
-  if (H.n_recorders > 0) {
+  if (H.n_recorders > 0 && sv.has_recorders(container, sel)) {
     const V3 lp = map_point(sv.node(container) + kNodeW2L, ph.p);
     tr.sel = sel; tr.node = container; tr.has_normal = false; tr.normal = V3{0.0, 0.0, 0.0}; tr.lp = lp; tr.cosine = 1.0;
   }
@@ -606,7 +606,7 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
     PVT_LOG_N(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, true, nw);
     sel = container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING;
   }
-  if (record) { tr.sel = sel; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c; }
+  if (record && sv.has_recorders(hit, sel)) { tr.sel = sel; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c; }
   return true;
 }
 

@@ -259,6 +259,10 @@ struct SceneView {
     const int word = hdr().off_rec_index + node * kRecSelectors + sel;
     start = ival(word, 0); count = ival(word, 1);
   }
+  // does any recorder listen to (node, selector)?  Events nobody listens to are not even handed to the tally
+  __device__ __forceinline__ bool has_recorders(int node, int sel) const {
+    return ival(hdr().off_rec_index + node * kRecSelectors + sel, 1) > 0;
+  }
   __device__ __forceinline__ int rec_candidate(int k) const { return reinterpret_cast<const int32_t*>(w + hdr().off_rec_list)[k]; }
   // recorders matching a surface event on local face `face` of a box node; count < 0: not pre-resolved
   __device__ __forceinline__ void face_range(int node, int sel, int face, int& start, int& count) const {
