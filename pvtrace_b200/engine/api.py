@@ -155,6 +155,16 @@ class EngineResult:
             yield history
 
 
+def _to_sqlite(self, dbfilepath, first_throw_id=0, end_rays=False):
+    """Write the logged histories into the reference CLI's database layout (engine/sinks.py)."""
+    from pvtrace_b200.engine import sinks
+
+    return sinks.write_sqlite(self, dbfilepath, first_throw_id=first_throw_id, end_rays=end_rays)
+
+
+EngineResult.to_sqlite = _to_sqlite
+
+
 def simulate(scene, num_rays, seed=None, workers=None, maxsteps=1000, max_events=128, emit_method="kT",
              record_every=1, *, rng="philox", device=None, first_index=0):
     """Trace `num_rays` through `scene` on the GPU.

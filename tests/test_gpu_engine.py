@@ -386,3 +386,25 @@ def test_service_warps_in_place_tallies_and_register_kernel_agree(gpu, monkeypat
             for key in ("rec_distinct", "rec_crossings", "rec_bins"):
                 assert (base[key] == other[key]).all(), (n, mode, key)
             np.testing.assert_allclose(base["rec_sums"], other["rec_sums"], rtol=1e-10, atol=1e-300)
+
+
+def test_device_histories_into_the_cli_database(gpu, tmp_path):
+    """EngineResult.to_sqlite (engine/sinks.py): the device's event log lands in the reference CLI's tables, one
+    (ray, event) row pair per logged event, and agrees with `histories()`."""
+    import sqlite3
+
+    scene = scenes.SCENES["mixed"]()
+    result = pv.engine.simulate(scene, 300, seed=4, record_every=1)
+    path = str(tmp_path / "run.sqlite3")
+    written = result.to_sqlite(path)
+    histories = list(result.histories())
+    assert written == sum(len(h) for h in histories) == int(result.data["counts"].sum())
+    connection = sqlite3.connect(path)
+    kinds = [r[0] for r in connection.execute("SELECT kind FROM event ORDER BY rowid")]
+    throws = [r[0] for r in connection.execute("SELECT throw_id FROM ray ORDER BY rowid")]
+    last = connection.execute("SELECT x, y, z, wavelength, source FROM ray ORDER BY rowid DESC LIMIT 1").fetchone()
+    connection.close()
+    assert kinds == [event.name for h in histories for _, event, _ in h]
+    assert throws == [j for j, h in enumerate(histories) for _ in h]
+    ray = histories[-1][-1][0]
+    assert tuple(last[:3]) == tuple(ray.position) and last[3] == ray.wavelength and last[4] == ray.source
