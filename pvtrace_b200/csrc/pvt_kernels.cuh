@@ -428,13 +428,12 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
 
   LaneStats st;
   double* const ring = S > 0 ? a.requests + (size_t)blockIdx.x * 2 * kReqWords * P : nullptr;  // two halves, by parity
-  if (S > 0 && tid >= T) {
+  const bool service = S > 0 && tid >= T;
+  if (service) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
     service_loop<P>(sv, sink, pool, ring, lane);
     __threadfence();
-    retire_cta(a, R, st);
-    return;
-  }
+  } else {  // the tracing warps; both roles meet again at retire_cta's barrier below
   if (S > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTracerRegs));
   uint32_t idle_iterations = 0;
 #ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
@@ -675,6 +674,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
     for (int k = 0; k < 4; ++k) atomicAdd(a.g_stats + 4 + k, (u64)prof[k]);
 #endif
 #endif
+  }  // tracing warps
   retire_cta(a, R, st);
 }
 
