@@ -160,7 +160,8 @@ enum { kCtrNext = 8, kCtrNextSnap = 9, kCtrRingHi = 10, kCtrRingHiPending = 11, 
        kCtrClaimed = 15, kCtrExhausted = 16 /* the global counter has run past n */, kCtrBlock = 17 /* [4] */,
        // service warps (tally requests): batch id published, requests in it, chunk cursor, chunks done, warps that
        // have left the batch, exit flag
-       kSvcBatch = 21, kSvcCount = 22, kSvcSteal = 23, kSvcDone = 24, kSvcAck = 25, kSvcExit = 26, kCtrCount = 27 };
+       kSvcBatch = 21, kSvcCount = 22, kSvcSteal = 23, kSvcDone = 24, kSvcAck = 25, kSvcExit = 26,
+       kSvcRayLo = 27, kSvcRayHi = 28 /* sequence entries the service warps are asked to put into the ring */, kCtrCount = 29 };
 static_assert(kCtrCount <= 32, "the counters live in 128 bytes");
 
 // photon index (within the bundle) of entry q of the CTA's sequence
@@ -360,19 +361,46 @@ __device__ __forceinline__ void write_request(double* ring, int stride, uint32_t
   q[7 * stride] = __longlong_as_double((long long)packed);
 }
 
-template <int P>
-__device__ __forceinline__ void service_loop(const SceneView& sv, const TallySink& sink, const PoolView& pool,
-                                             const double* ring, int lane) {
+// entry o of the CTA's sequence into the ring of fresh rays (K entries, seven columns)
+// kArraysOnly: the caller never emits (the service warps: the emitter's code inside their reduced register allocation
+// crashes ptxas 12.9, so on-device emission stays with the tracing warps)
+template <int K, bool kArraysOnly = false>
+__device__ __forceinline__ void produce_ray(const TraceArgs& a, const SceneView& sv, const PoolView& pool, uint32_t o) {
+  const long long i = sequence_photon(pool.counters, o);
+  double* r = pool.ring + (o & (K - 1));
+  if (a.pos) {
+    // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles);
+    // L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived
+    r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2);
+    r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2);
+    r[6 * K] = __ldcg(a.wl + i);
+  } else if (!kArraysOnly) {
+    emit_ray_to_ring(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i, r, K);
+  }
+}
+
+template <int P, int K>
+__device__ __forceinline__ void service_loop(const TraceArgs& a, const SceneView& sv, const TallySink& sink,
+                                             const PoolView& pool, const double* ring, int lane) {
   for (;;) {
     // sleep on named barrier 2 until warp 0 of the tracers arrives with a batch (or with the exit flag): no polling
     asm volatile("bar.sync 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
     if (peek(pool.counters + kSvcExit)) return;
     const uint32_t batch = peek(pool.counters + kSvcBatch);
     const uint32_t count = peek(pool.counters + kSvcCount), chunks = (count + 31u) >> 5;
-    const double* half = ring + (size_t)((batch - 1u) & 1u) * kReqWords * P;  // batch b was written in iteration b - 1
+    const uint32_t ray_lo = peek(pool.counters + kSvcRayLo), ray_hi = peek(pool.counters + kSvcRayHi);
+    const uint32_t ray_chunks = (ray_hi - ray_lo + 31u) >> 5;
+    const double* half = ring + (size_t)(batch & 1u) * kReqWords * P;  // batch b = requests of iteration b - 2
     for (;;) {
-      const uint32_t chunk = steal_chunk(pool.counters + kSvcSteal, lane);
-      if (chunk >= chunks) break;
+      uint32_t chunk = steal_chunk(pool.counters + kSvcSteal, lane);
+      if (chunk >= ray_chunks + chunks) break;
+      if (chunk < ray_chunks) {  // fresh rays first: the tracing warps refill from them next iteration
+        const uint32_t o = ray_lo + chunk * 32u + (uint32_t)lane;
+        if (o < ray_hi) produce_ray<K, true>(a, sv, pool, o);
+        __syncwarp();
+        continue;
+      }
+      chunk -= ray_chunks;
       const uint32_t at = chunk * 32u + (uint32_t)lane;
       if (at < count) {
         const double* q = half + at;
@@ -429,9 +457,10 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   LaneStats st;
   double* const ring = S > 0 ? a.requests + (size_t)blockIdx.x * 2 * kReqWords * P : nullptr;  // two halves, by parity
   const bool service = S > 0 && tid >= T;
+  const bool svc_rays = S > 0 && a.pos != nullptr;  // the service warps also fill the ring of fresh rays (arrays only)
   if (service) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
-    service_loop<P>(sv, sink, pool, ring, lane);
+    service_loop<P, K>(a, sv, sink, pool, ring, lane);
     __threadfence();
   } else {  // the tracing warps; both roles meet again at retire_cta's barrier below
   if (S > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTracerRegs));
@@ -450,17 +479,30 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
     // Every warp takes chunks from one shared counter until the stage's work list is empty, so no warp has a
     // fixed share: classification chunks first (long), ray production chunks last (short).
     bool live = false;
-    if (S > 0 && iter > 0 && tid < 32) {
-      // Warp 0 publishes the requests written by the stage 2 that just ended (its barrier made them visible) and
-      // wakes the service warps.  Batch b is written in stage 2 of iteration b - 1 into ring half (b - 1) & 1 and
-      // served during iteration b -- a whole iteration of slack -- so the wait for the PREVIOUS batch's
-      // acknowledgements almost never spins.
+    if (S > 0 && tid < 32) {
+      // Warp 0 hands the service warps their work for this iteration and wakes them: the tally requests written by
+      // the stage 2 that just ended (its barrier made them visible; ring half by parity) and the next stretch of
+      // fresh rays to put into the ring.  They have the whole iteration for it, so the wait for the PREVIOUS
+      // hand-over's acknowledgements almost never spins; once it is in, what was asked for then is in the ring.
       if (tid == 0) {
         while (peek(pool.counters + kSvcAck) < (uint32_t)kSvcWarps) { }
         pool.counters[kSvcAck] = 0u;
+        if (svc_rays) {
+          const uint32_t produced = pool.counters[kSvcRayHi], next = pool.counters[kCtrNextSnap];
+          // (the other warps may still read the old value this iteration: they then fetch those rays themselves)
+          pool.counters[kCtrRingHi] = produced;
+          // to produce: [max(produced, next), next + K), none beyond what has arrived; `next` is the snapshot taken
+          // at the last barrier, so ring entries that this iteration's refills read are never overwritten
+          const uint32_t lo = produced > next ? produced : next, avail = pool.counters[kCtrAvail];
+          uint32_t hi = next + (uint32_t)K;
+          if (hi > avail) hi = avail;
+          if (hi < lo) hi = lo;
+          pool.counters[kSvcRayLo] = lo;
+          pool.counters[kSvcRayHi] = hi;
+        }
         pool.counters[kSvcCount] = pool.counters[4 * ((iter + 1) & 1) + 2];
         pool.counters[kSvcSteal] = 0u;
-        pool.counters[kSvcBatch] = iter;
+        pool.counters[kSvcBatch] = iter + 1u;
         __threadfence_block();
       }
       __syncwarp();
@@ -476,9 +518,9 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
       uint32_t hi = next + (uint32_t)K;
       if (hi > avail) hi = avail;
       if (hi < lo) hi = lo;
-      const uint32_t classify_chunks = P / 32, ray_chunks = (hi - lo + 31u) >> 5;
+      const uint32_t classify_chunks = P / 32, ray_chunks = svc_rays ? 0u : (hi - lo + 31u) >> 5;
       if (tid == 0) {
-        pool.counters[kCtrRingHiPending] = hi;
+        if (!svc_rays) pool.counters[kCtrRingHiPending] = hi;
         pool.counters[kCtrSteal + 1] = 0u;  // stage 2's work counter
       }
       for (;;) {
@@ -488,20 +530,8 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         // when the caller's arrays are page-locked) and the warp that waits for them simply takes fewer
         // classification chunks afterwards (10.33 -> 10.19 ms on config 2 against producing last).
         if (chunk < ray_chunks) {
-          const uint32_t o = lo + chunk * 32u + (uint32_t)lane;  // slice offset of this lane's ray
-          if (o < hi) {
-            const long long i = sequence_photon(pool.counters, o);
-            double* r = pool.ring + (o & (K - 1));
-            if (a.pos) {
-              // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles);
-              // L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived
-              r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2);
-              r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2);
-              r[6 * K] = __ldcg(a.wl + i);
-            } else {
-              emit_ray_to_ring(sv, id0 + (u64)i, a.first_index + i, r, K);
-            }
-          }
+          const uint32_t o = lo + chunk * 32u + (uint32_t)lane;  // sequence entry of this lane's ray
+          if (o < hi) produce_ray<K>(a, sv, pool, o);
           continue;
         }
         chunk -= ray_chunks;
@@ -586,7 +616,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
     const uint32_t nv = (cv + 31u) >> 5, ns = (cs + 31u) >> 5, ne = (ce + 31u) >> 5;
     if (tid < 4) pool.counters[4 * ((iter + 1) & 1) + tid] = 0u;
     if (tid == T - 1) {  // publish the cursors for the next iteration (nobody refills or produces in stage 2)
-      pool.counters[kCtrRingHi] = pool.counters[kCtrRingHiPending];
+      if (!svc_rays) pool.counters[kCtrRingHi] = pool.counters[kCtrRingHiPending];
       pool.counters[kCtrNextSnap] = pool.counters[kCtrNext];
       extend_sequence(a, pool.counters, (uint32_t)K);
       pool.counters[kCtrSteal] = 0u;  // stage 1's work counter
