@@ -362,9 +362,10 @@ __device__ __forceinline__ void write_request(double* ring, int stride, uint32_t
 }
 
 // entry o of the CTA's sequence into the ring of fresh rays (K entries, seven columns)
-// kArraysOnly: the caller never emits (the service warps: the emitter's code inside their reduced register allocation
-// crashes ptxas 12.9, so on-device emission stays with the tracing warps)
-template <int K, bool kArraysOnly = false>
+// kInlineEmitter: the service warps inline the emitter (no out-of-line call inside their reduced register allocation;
+// the emitter itself takes sin(cone angle) from the light record -- sin()'s slow path inside a setmaxnreg region
+// crashes ptxas 12.9)
+template <int K, bool kInlineEmitter = false>
 __device__ __forceinline__ void produce_ray(const TraceArgs& a, const SceneView& sv, const PoolView& pool, uint32_t o) {
   const long long i = sequence_photon(pool.counters, o);
   double* r = pool.ring + (o & (K - 1));
@@ -374,7 +375,12 @@ __device__ __forceinline__ void produce_ray(const TraceArgs& a, const SceneView&
     r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2);
     r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2);
     r[6 * K] = __ldcg(a.wl + i);
-  } else if (!kArraysOnly) {
+  } else if (kInlineEmitter) {
+    const EmittedRay e = emit_ray_value(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i);
+    r[0] = e.pos.x; r[K] = e.pos.y; r[2 * K] = e.pos.z;
+    r[3 * K] = e.dir.x; r[4 * K] = e.dir.y; r[5 * K] = e.dir.z;
+    r[6 * K] = e.wl;
+  } else {
     emit_ray_to_ring(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i, r, K);
   }
 }
@@ -457,7 +463,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   LaneStats st;
   double* const ring = S > 0 ? a.requests + (size_t)blockIdx.x * 2 * kReqWords * P : nullptr;  // two halves, by parity
   const bool service = S > 0 && tid >= T;
-  const bool svc_rays = S > 0 && a.pos != nullptr;  // the service warps also fill the ring of fresh rays (arrays only)
+  const bool svc_rays = S > 0;  // the service warps also fill the ring of fresh rays
   if (service) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
     service_loop<P, K>(a, sv, sink, pool, ring, lane);

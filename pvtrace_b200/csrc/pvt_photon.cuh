@@ -673,7 +673,7 @@ __device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, u64 id
     const double u0 = u53(b2.x, b2.y), u1 = u53(b2.z, b2.w);
     switch (kind) {
       case PVT_LDIR_CONE: {
-        const double st = sqrt(u0) * sin(prm);
+        const double st = sqrt(u0) * q[kLightSinDir];  // sin(prm), taken once on the host
         ld = polar_sc(st, sqrt(fmax(1.0 - st * st, 0.0)), u1);
       } break;
       case PVT_LDIR_ISOTROPIC: {

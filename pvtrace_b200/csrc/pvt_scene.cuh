@@ -24,6 +24,7 @@
 //               node whose faces cannot be pre-resolved (not a box, or a facet within 1e-9 of its tolerance)
 //   face_list   int32 recorder indices
 #pragma once
+#include <math.h>
 #include <stdint.h>
 #include <string.h>
 #include <vector>
@@ -58,7 +59,8 @@ constexpr int kHistLoA = 0, kHistHiA = 1, kHistLoB = 2, kHistHiB = 3, kHistInts 
 constexpr int kFacetNormal = 0, kFacetAtol = 3, kFacetRefl = 4, kFacetInts = 5, kFacetWords = 8;
 // light record: l2w rows 0-2 (12) | pos_param (3) | dir_param | wl_param | ints: pos_kind,dir_kind | wl_kind,wl_start | wl_n,pad
 constexpr int kRecSelectors = 8;  // PVT_REC_* selectors 0..6, padded to 8
-constexpr int kLightL2W = 0, kLightPos = 12, kLightDir = 15, kLightWl = 16, kLightInts = 17, kLightWords = 20;
+constexpr int kLightL2W = 0, kLightPos = 12, kLightDir = 15, kLightWl = 16, kLightInts = 17, kLightSinDir = 20 /* sin(dir_param) */,
+              kLightWords = 22;
 
 // 1/dx when xs[0..n) is a uniform ascending grid (every knot within 1e-9 dx of xs[0] + i dx, so multiplying by
 // 1/dx stands in for dividing by the local spacing, and a guessed bracket is at most one knot off).  0 otherwise.
@@ -172,6 +174,7 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
     memcpy(q + kLightL2W, E->light_to_world + 16 * l, 12 * sizeof(double));
     q[kLightPos] = E->pos_param[3 * l]; q[kLightPos + 1] = E->pos_param[3 * l + 1]; q[kLightPos + 2] = E->pos_param[3 * l + 2];
     q[kLightDir] = E->dir_param[l]; q[kLightWl] = E->wl_param[l];
+    q[kLightSinDir] = sin(E->dir_param[l]);
     const size_t iw = h.off_lights + (size_t)l * kLightWords + kLightInts;
     put_ints(blob, iw, E->pos_kind[l], E->dir_kind[l]);
     put_ints(blob, iw + 1, E->wl_kind[l], E->wl_start[l]);
