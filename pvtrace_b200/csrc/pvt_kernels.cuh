@@ -490,29 +490,36 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
       // the stage 2 that just ended (its barrier made them visible; ring half by parity) and the next stretch of
       // fresh rays to put into the ring.  They have the whole iteration for it, so the wait for the PREVIOUS
       // hand-over's acknowledgements almost never spins; once it is in, what was asked for then is in the ring.
+      uint32_t work = 0;
       if (tid == 0) {
         while (peek(pool.counters + kSvcAck) < (uint32_t)kSvcWarps) { }
-        pool.counters[kSvcAck] = 0u;
+        uint32_t lo = 0, hi = 0;
         if (svc_rays) {
           const uint32_t produced = pool.counters[kSvcRayHi], next = pool.counters[kCtrNextSnap];
           // (the other warps may still read the old value this iteration: they then fetch those rays themselves)
           pool.counters[kCtrRingHi] = produced;
           // to produce: [max(produced, next), next + K), none beyond what has arrived; `next` is the snapshot taken
           // at the last barrier, so ring entries that this iteration's refills read are never overwritten
-          const uint32_t lo = produced > next ? produced : next, avail = pool.counters[kCtrAvail];
-          uint32_t hi = next + (uint32_t)K;
+          lo = produced > next ? produced : next;
+          const uint32_t avail = pool.counters[kCtrAvail];
+          hi = next + (uint32_t)K;
           if (hi > avail) hi = avail;
           if (hi < lo) hi = lo;
           pool.counters[kSvcRayLo] = lo;
           pool.counters[kSvcRayHi] = hi;
         }
-        pool.counters[kSvcCount] = pool.counters[4 * ((iter + 1) & 1) + 2];
-        pool.counters[kSvcSteal] = 0u;
-        pool.counters[kSvcBatch] = iter + 1u;
-        __threadfence_block();
+        const uint32_t count = pool.counters[4 * ((iter + 1) & 1) + 2];
+        work = count + (hi - lo);
+        if (work) {  // nothing to hand over (a draining or starving CTA): the service warps sleep on
+          pool.counters[kSvcAck] = 0u;
+          pool.counters[kSvcCount] = count;
+          pool.counters[kSvcSteal] = 0u;
+          pool.counters[kSvcBatch] = iter + 1u;
+          __threadfence_block();
+        }
       }
-      __syncwarp();
-      asm volatile("bar.arrive 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
+      work = __shfl_sync(kFullMask, work, 0);
+      if (work) asm volatile("bar.arrive 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
     }
     {
       const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
