@@ -331,6 +331,7 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
 // whether it is the photon's first, batches are served in order and a slot appears once per batch.  The tracing
 // warps synchronise among themselves on a named barrier, and the registers of the CTA are re-divided between the
 // two roles (setmaxnreg).
+constexpr int kDrainPhotons = 96;  // a CTA with no supply left and at most this many live photons drains them lane by lane
 constexpr int kReqWords = 8;
 constexpr int kSvcWarps = 4;
 constexpr int kTracerRegs = 104, kSvcRegs = 64;  // 512 x 104 + 128 x 64 = 640 x 96, what the CTA is launched with (the pool is per CTA)
@@ -471,6 +472,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   } else {  // the tracing warps; both roles meet again at retire_cta's barrier below
   if (S > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTracerRegs));
   uint32_t idle_iterations = 0;
+  bool draining = false;
 #ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
   long long prof[4] = {0, 0, 0, 0}, prof_t = clock64();
   u64 prof_start;
@@ -521,6 +523,21 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
       work = __shfl_sync(kFullMask, work, 0);
       if (work) asm volatile("bar.arrive 2, %0;" ::"n"(kSvcWarps * 32 + 32) : "memory");
     }
+#ifndef PVT_NO_DRAIN
+    if (iter > 0) {
+      // The last photons of a CTA: no ray will ever be refilled and few slots are live (the previous iteration's
+      // queue lengths, still in place, bound their number).  Two barriers and two rounds of work stealing per step
+      // are then pure latency in front of a handful of serial chains: leave the loop and let every thread run the
+      // photons of its own slots to their ends (below).
+      const uint32_t* prev = pool.counters + 4 * ((iter + 1) & 1);
+      const uint32_t live_before = (prev[0] & 0xffffu) + (prev[0] >> 16) + prev[1];
+      if (live_before <= (uint32_t)kDrainPhotons && pool.counters[kCtrExhausted] &&
+          pool.counters[kCtrNextSnap] >= pool.counters[kCtrClaimed]) {
+        draining = true;
+        break;
+      }
+    }
+#endif
     {
       const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
       // rays to produce: [max(ring_hi, next), next + K), `next` being the snapshot taken at the last barrier, so
@@ -693,6 +710,42 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
     sync_tracers<T, S>();
     PVT_PROF(3);
   }
+#ifndef PVT_NO_DRAIN
+  if (draining) {
+    // ---------------- drain: one photon per lane, whole steps, no barriers, tallies in place --------------------
+    if (S > 0) {  // the seen masks come back from the service warps once their last batch is done
+      sync_tracers<T, S>();  // ... which warp 0 has handed over by the time it gets here
+      if (lane == 0) while (peek(pool.counters + kSvcAck) < (uint32_t)kSvcWarps) { }
+      __syncwarp();
+      __threadfence_block();
+    }
+    for (int slot = tid; slot < P; slot += T) {
+      if (pool.count[slot] < 0) continue;
+      PoolPhoton ph;
+      load_slot<kLog, S == 0>(pool, slot, ph, sp.max_events);
+      if (S > 0 && pool.tallied[slot]) {
+        const u64 seen = pool.seen[slot];
+        ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
+      }
+      PhiloxStream rng;
+      rng.id = id0 + (u64)pool.idx[slot];
+      for (;;) {
+        StepPlan plan;
+        const StepClass cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan);
+        bool alive = false;
+        TallyReq tr;
+        if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+        else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+        else if (cls == kExit) exit_step<kLog>(sv, L, sp, ph, st, plan, tr);
+        else if (cls == kKill) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
+        if (tr.sel >= 0) tally(sv, sink, ph, tr);
+        if (!alive) break;
+      }
+      if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
+      pool.count[slot] = -1;
+    }
+  }
+#endif
   if (S > 0 && tid < 32) {  // the last batch was published at the top of the final iteration
     if (tid == 0) {
       while (peek(pool.counters + kSvcAck) < (uint32_t)kSvcWarps) { }
