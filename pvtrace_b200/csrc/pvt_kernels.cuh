@@ -331,7 +331,10 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
 // whether it is the photon's first, batches are served in order and a slot appears once per batch.  The tracing
 // warps synchronise among themselves on a named barrier, and the registers of the CTA are re-divided between the
 // two roles (setmaxnreg).
-constexpr int kDrainPhotons = 96;  // a CTA with no supply left and at most this many live photons drains them lane by lane
+#ifndef PVT_DRAIN_PHOTONS
+#define PVT_DRAIN_PHOTONS 32  // (32 / 96 / 256 / 512 measured 6.45 / 6.51 / 6.51 / 6.56 ms on config 2)
+#endif
+constexpr int kDrainPhotons = PVT_DRAIN_PHOTONS;  // a CTA with no supply left and at most this many live photons drains them lane by lane
 constexpr int kReqWords = 8;
 constexpr int kSvcWarps = 4;
 constexpr int kTracerRegs = 104, kSvcRegs = 64;  // 512 x 104 + 128 x 64 = 640 x 96, what the CTA is launched with (the pool is per CTA)
