@@ -169,7 +169,7 @@ __device__ __forceinline__ Nearest nearest_surface(const SceneView& sv, const V3
 
 // The same reduction for scenes made of axis-aligned boxes only (every LSC scene: world box, slab, coatings), chosen
 // per scene by the kernels' kBoxes instantiation: no primitive switch, no rotation, one reciprocal direction for all.
-__device__ __forceinline__ Nearest nearest_surface_boxes(const SceneView& sv, const V3& p, const V3& d) {
+__device__ __noinline__ Nearest nearest_surface_boxes_any(const SceneView sv, V3 p, V3 d) {  // rays parallel to a slab: rare
   const int n_nodes = sv.hdr().n_nodes;
   TwoNearest best;
   const V3 inv = slab_reciprocal(d);
@@ -179,6 +179,34 @@ __device__ __forceinline__ Nearest nearest_surface_boxes(const SceneView& sv, co
     double t_in, t_out;
     bool ok_in, ok_out;
     box_roots(rec[kNodeHalf], rec[kNodeHalf + 1], rec[kNodeHalf + 2], o, d, inv, t_in, t_out, ok_in, ok_out);
+    best.add_pair(t_in, t_out, node, ok_in, ok_out);
+  }
+  return best.result();
+}
+__device__ __forceinline__ Nearest nearest_surface_boxes(const SceneView& sv, const V3& p, const V3& d) {
+  if (slab_parallel(d)) return nearest_surface_boxes_any(sv, p, d);  // (the direction is the same in every node's frame)
+  const int n_nodes = sv.hdr().n_nodes;
+  const V3 inv = slab_reciprocal(d);
+  const double* rec = sv.node(0);
+  TwoNearest best;
+  {  // node 0 straight into the empty reduction: what add_pair would select against +inf sentinels
+    const V3 o = V3{p.x + rec[kNodeW2L + 3], p.y + rec[kNodeW2L + 7], p.z + rec[kNodeW2L + 11]};
+    double t_in, t_out;
+    bool ok_in, ok_out;
+    box_roots_oblique(rec[kNodeHalf], rec[kNodeHalf + 1], rec[kNodeHalf + 2], o, d, inv, t_in, t_out, ok_in, ok_out);
+    best.t_first = ok_in ? t_in : (ok_out ? t_out : PVT_INF);
+    best.n_first = ok_out ? 0 : -1;  // ok_in implies ok_out
+    best.t_second = ok_in ? t_out : PVT_INF;
+    best.n_second = ok_in ? 0 : -1;
+    best.t_single = (ok_out && !ok_in) ? t_out : PVT_INF;
+    best.n_single = (ok_out && !ok_in) ? 0 : -1;
+  }
+  rec += kNodeWords;
+  for (int node = 1; node < n_nodes; ++node, rec += kNodeWords) {
+    const V3 o = V3{p.x + rec[kNodeW2L + 3], p.y + rec[kNodeW2L + 7], p.z + rec[kNodeW2L + 11]};
+    double t_in, t_out;
+    bool ok_in, ok_out;
+    box_roots_oblique(rec[kNodeHalf], rec[kNodeHalf + 1], rec[kNodeHalf + 2], o, d, inv, t_in, t_out, ok_in, ok_out);
     best.add_pair(t_in, t_out, node, ok_in, ok_out);
   }
   return best.result();

@@ -408,3 +408,31 @@ def test_device_histories_into_the_cli_database(gpu, tmp_path):
     assert throws == [j for j, h in enumerate(histories) for _ in h]
     ray = histories[-1][-1][0]
     assert tuple(last[:3]) == tuple(ray.position) and last[3] == ray.wavelength and last[4] == ray.source
+
+
+def test_event_logs_do_not_depend_on_who_tallies_or_on_the_drain(gpu, monkeypatch):
+    """Bundles small enough that most of the run is the drain (a CTA with no supply left finishes its photons lane by
+    lane), every ray logged: the three kernels -- service warps, in-place tallies, one photon per lane -- write the
+    same event log row for row and the same tallies."""
+    scene = scenes.SCENES["lsc"]()
+    compiled, emitter = pv.engine.compile_scene(scene), pv.engine.compile_emitter(scene)
+    for n in (40, 1500):
+        results = {}
+        for mode in ("service", "in_place", "register"):
+            monkeypatch.setenv("PVT_TALLY_IN_PLACE", "1" if mode == "in_place" else "0")
+            with _cuda.Context(compiled, emitter, 0) as ctx:
+                ctx.reset()
+                ctx.trace(n, 33, record_every=1, max_events=256,
+                          flags=_cuda.FLAG_REGISTER_KERNEL if mode == "register" else 0)
+                results[mode] = ctx.read()
+        base = results["service"]
+        assert base["counts"].min() >= 2
+        for mode in ("in_place", "register"):
+            other = results[mode]
+            assert (other["counts"] == base["counts"]).all(), (n, mode)
+            for key in ("kind", "hit", "container", "adjacent", "component"):
+                assert (other[key] == base[key]).all(), (n, mode, key)
+            for key in ("position", "wavelength", "travelled"):
+                np.testing.assert_allclose(other[key], base[key], rtol=1e-12, atol=1e-12, err_msg=f"{n} {mode} {key}")
+            for key in ("rec_distinct", "rec_crossings", "rec_bins"):
+                assert (other[key] == base[key]).all(), (n, mode, key)
