@@ -1,19 +1,21 @@
 // pvt_kernels.cuh -- the CUDA kernels of libpvtrace_b200.so (sm_100a).
 //
-//   wavefront_kernel  THE tracer.  Persistent CTAs (one per SM) that each own a contiguous slice of the photon
-//                     index range and a pool of live photons held as a structure of arrays in SHARED MEMORY.
-//                     Every loop iteration runs two barrier-separated stages over the pool:
-//                       1. refill + classify: each pool slot is served by its home thread; retired slots take the
-//                          next photon of the slice (coalesced load of the initial-ray arrays, or on-device
-//                          emission); live photons are intersected with every node and draw their free path;
-//                          the slot index is appended to the VOLUME, SURFACE or EXIT queue (warp ballot +
-//                          one shared-memory atomic per warp);
-//                       2. interact: the three queues are laid end to end, padded to warp boundaries, and
-//                          thread e serves entry e -- so every warp executes ONE kind of interaction with all
-//                          lanes busy, instead of every warp executing all kinds with a few lanes each.
-//                     The scene blob is staged into shared memory once per CTA by a single TMA bulk copy
-//                     (cp.async.bulk + mbarrier).  Random numbers are addressed by (photon, step, purpose), so
-//                     neither the regrouping nor the CTA count is visible in the results.
+//   wavefront_kernel  THE tracer.  Persistent CTAs (one per SM) around a pool of live photons held as a structure of
+//                     arrays in SHARED MEMORY; CTAs claim blocks of photons from a global counter as their pools
+//                     drain.  Every loop iteration of the 16 tracing warps runs two barrier-separated stages, in
+//                     both of which every warp takes chunks of 32 work items from a shared counter:
+//                       1. refill + classify: retired slots take the next ray from a shared-memory ring of fresh
+//                          rays; live photons draw the step's uniforms, are intersected with every node and get
+//                          their free path; the slot index is appended to the VOLUME, SURFACE or EXIT queue (warp
+//                          ballots + one or two shared-memory atomics per warp);
+//                       2. interact: the queues are cut into chunks of 32 entries, so every warp executes ONE kind
+//                          of interaction with all lanes busy, instead of all kinds with a few lanes each; an
+//                          event to be tallied only writes a 64-byte request.
+//                     A fifth warpgroup (service warps) tallies the requests an iteration later and keeps the ray
+//                     ring filled (array loads or on-device emission).  The last photons of a CTA are drained
+//                     lane by lane without barriers.  The scene blob is staged into shared memory once per CTA by a
+//                     single TMA bulk copy (cp.async.bulk + mbarrier).  Random numbers are addressed by (photon,
+//                     step, purpose), so neither the regrouping nor the CTA count is visible in the results.
 //   trace_kernel      the same physics with one photon per lane held in registers (persistent threads, warp
 //                     ballot refill from a global counter).  Handles everything the pool kernel does not:
 //                     the reference's sequential xoshiro stream, more than 64 recorders, scenes too large for
@@ -181,7 +183,7 @@ struct PoolView {
   uint32_t *idx, *ids;
   uint16_t *qv, *qs, *qe;
   uint8_t* tallied;    // service-warp kernels: this photon has sent a tally request before (its seen mask is live)
-  double* ring;        // [7][K]: px py pz dx dy dz wl of photons [ring_lo, ring_hi) of the slice, at offset mod K
+  double* ring;        // [7][K]: px py pz dx dy dz wl of entries [.., ring_hi) of the CTA's ray sequence, at entry mod K
   uint32_t* counters;
 };
 
@@ -486,9 +488,9 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
 #endif
   for (uint32_t iter = 0;; ++iter) {
     uint32_t* qn = pool.counters + 4 * (iter & 1);  // queue lengths of this iteration: VOLUME | SURFACE << 16, EXIT
-    // ---------------- stage 1: refill + classify the pool, 32 slots per chunk; then produce fresh rays --------
+    // ---------------- stage 1: refill + classify the pool, 32 slots per chunk ----------------------------------
     // Every warp takes chunks from one shared counter until the stage's work list is empty, so no warp has a
-    // fixed share: classification chunks first (long), ray production chunks last (short).
+    // fixed share (kernels without service warps also produce the fresh rays here, first).
     bool live = false;
     if (S > 0 && tid < 32) {
       // Warp 0 hands the service warps their work for this iteration and wakes them: the tally requests written by
@@ -542,12 +544,12 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
     }
 #endif
     {
-      const uint32_t ring_hi = pool.counters[kCtrRingHi];  // rays [.., ring_hi) of the slice are in the ring
+      const uint32_t ring_hi = pool.counters[kCtrRingHi];  // entries [.., ring_hi) of the sequence are in the ring
       // rays to produce: [max(ring_hi, next), next + K), `next` being the snapshot taken at the last barrier, so
       // ring entries read by this stage's refills are never overwritten
       const uint32_t next = pool.counters[kCtrNextSnap];
       const uint32_t lo = ring_hi > next ? ring_hi : next;
-      const uint32_t avail = pool.counters[kCtrAvail];  // <= slice_n
+      const uint32_t avail = pool.counters[kCtrAvail];  // claimed and arrived
       uint32_t hi = next + (uint32_t)K;
       if (hi > avail) hi = avail;
       if (hi < lo) hi = lo;
@@ -633,7 +635,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         }
       }
     }
-    // leave when no slot is live and every ray of the slice has been taken; while rays are still in flight from
+    // leave when no slot is live and every claimed ray has been taken with nothing left to claim; while rays are still in flight from
     // the host the CTA keeps polling (bounded: a transfer that never completes must not hang the device)
     const bool pending = !(pool.counters[kCtrExhausted] && pool.counters[kCtrNextSnap] >= pool.counters[kCtrClaimed]) &&
                          idle_iterations < kMaxIdleIterations;
