@@ -550,7 +550,8 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
       if (Rng::kAddressed) { u_gamma = u_gamma_early; u_delay = u_delay_early; }
       else u_gamma = rng.one(kBlockEmit, 0);
       const double gamma = p1 + (1.0 - p1) * u_gamma;
-      ph.wl = interp(gamma, ec, ex, en);
+      ph.wl = sv.comp_int(comp, CI_HAS_GUIDE) ? interp_guided(gamma, ec, ex, en, sv.ems_guide(comp), kGuideBuckets)
+                                              : interp(gamma, ec, ex, en);
       if (cr[kCompTauRad] > 0.0) {
         if (!Rng::kAddressed) u_delay = rng.one(kBlockEmit, 1);
         ph.duration += -log(1.0 - u_delay) * cr[kCompTauRad];

@@ -23,6 +23,8 @@
 //               test against the face's world normal is done once here instead of per event; count < 0 marks a
 //               node whose faces cannot be pre-resolved (not a box, or a facet within 1e-9 of its tolerance)
 //   face_list   int32 recorder indices
+//   ems_guide   per emitting component, kGuideBuckets + 1 uint16: guide[b] = last knot i with ems_cdf[i] <= b / kGuideBuckets
+//               (0 if none), so the inverse-CDF lookup bisects a bracket of a knot or two instead of the whole table
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -37,7 +39,7 @@ struct Header {
   int32_t n_nodes, root_id, n_components, n_recorders, n_hists, total_bins, n_facets, n_lights;
   int32_t off_nodes, off_comps, off_abs_x, off_abs_y, off_ems_x, off_ems_cdf, off_recs, off_hists;
   int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, off_rec_index, off_rec_list, off_face_index;
-  int32_t off_face_list, pad3, pad4, pad5;
+  int32_t off_face_list, off_ems_guide, pad4, pad5;
 };
 constexpr int kHeaderWords = sizeof(Header) / 8;
 static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
@@ -48,7 +50,9 @@ static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for 
 constexpr int kNodeW2L = 0, kNodeL2W = 12, kNodeParams = 24, kNodeIndex = 28, kNodeInts = 29, kNodeSlowness = 32,
               kNodeHalf = 34, kNodeWords = 38;
 // component record: qy, tau_rad, tau_nr, phase_param | ints: type,phase_type | abs_start,abs_n | ems_start,ems_n |
-// abs_inv_dx, ems_inv_dx (1/spacing of the x grid when it is uniform enough for interp_hinted, else 0) | pad
+// abs_inv_dx, ems_inv_dx (1/spacing of the x grid when it is uniform enough for interp_hinted, else 0) |
+// ints: guide_start (uint16 index into ems_guide), has_guide
+constexpr int kGuideBuckets = 256;
 constexpr int kCompQy = 0, kCompTauRad = 1, kCompTauNr = 2, kCompPhaseParam = 3, kCompInts = 4, kCompAbsInvDx = 7,
               kCompEmsInvDx = 8, kCompWords = 10;
 // recorder record: facet xyz, atol | ints: node,event | has_facet,hist_start | hist_n,pad | pad
@@ -105,6 +109,7 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
   h.off_face_index = w; w += S.n_nodes * kRecSelectors * 6;
   // worst case every recorder of a node matches all six faces
   h.off_face_list = w; w += (6 * S.n_recorders + 1) / 2;
+  h.off_ems_guide = w; w += (S.n_components * (kGuideBuckets + 1) + 3) / 4;
   w = (w + 1) & ~1;
   h.total_words = w;
 
@@ -137,6 +142,22 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
     put_ints(blob, iw + 2, S.comp_ems_start[c], S.comp_ems_n[c]);
     r[kCompAbsInvDx] = uniform_inv_dx(S.abs_x + S.comp_abs_start[c], S.comp_abs_n[c]);
     r[kCompEmsInvDx] = S.comp_ems_n[c] > 0 ? uniform_inv_dx(S.ems_x + S.comp_ems_start[c], S.comp_ems_n[c]) : 0.0;
+    {  // guide table of the inverse CDF: valid for a non-decreasing cdf that ends at or below 1
+      const int n = S.comp_ems_n[c];
+      const double* cdf = S.ems_cdf + S.comp_ems_start[c];
+      bool ok = n >= 2 && n < 65535 && cdf[n - 1] <= 1.0;
+      for (int i = 1; i < n && ok; ++i) ok = cdf[i] >= cdf[i - 1];
+      uint16_t* guide = reinterpret_cast<uint16_t*>(&blob[h.off_ems_guide]) + (size_t)c * (kGuideBuckets + 1);
+      if (ok) {
+        int i = 0;
+        for (int b = 0; b <= kGuideBuckets; ++b) {
+          const double edge = (double)b / kGuideBuckets;
+          while (i + 1 < n && cdf[i + 1] <= edge) ++i;
+          guide[b] = (uint16_t)((cdf[i] <= edge) ? i : 0);
+        }
+      }
+      put_ints(blob, iw + 5, c * (kGuideBuckets + 1), ok ? 1 : 0);
+    }
   }
   if (S.n_abs_knots) {
     memcpy(&blob[h.off_abs_x], S.abs_x, S.n_abs_knots * sizeof(double));
@@ -251,6 +272,9 @@ struct SceneView {
   __device__ __forceinline__ int node_int(int i, int k) const { return ival(hdr().off_nodes + i * kNodeWords + kNodeInts + (k >> 1), k & 1); }
   __device__ __forceinline__ const double* comp(int c) const { return w + hdr().off_comps + c * kCompWords; }
   __device__ __forceinline__ int comp_int(int c, int k) const { return ival(hdr().off_comps + c * kCompWords + kCompInts + (k >> 1), k & 1); }
+  __device__ __forceinline__ const uint16_t* ems_guide(int c) const {
+    return reinterpret_cast<const uint16_t*>(w + hdr().off_ems_guide) + comp_int(c, 10 /* CI_GUIDE_START */);
+  }
   __device__ __forceinline__ const double* rec(int r) const { return w + hdr().off_recs + r * kRecWords; }
   __device__ __forceinline__ int rec_int(int r, int k) const { return ival(hdr().off_recs + r * kRecWords + kRecInts + (k >> 1), k & 1); }
   __device__ __forceinline__ const double* hist(int h) const { return w + hdr().off_hists + h * kHistWords; }
@@ -279,7 +303,8 @@ struct SceneView {
 // int slots of the records
 enum { NI_GEOM = 0, NI_SURF = 1, NI_COMP_START = 2, NI_COMP_COUNT = 3, NI_FACET_START = 4, NI_FACET_COUNT = 5,
        NI_ALIGNED = 8 };
-enum { CI_TYPE = 0, CI_PHASE = 1, CI_ABS_START = 2, CI_ABS_N = 3, CI_EMS_START = 4, CI_EMS_N = 5 };
+enum { CI_TYPE = 0, CI_PHASE = 1, CI_ABS_START = 2, CI_ABS_N = 3, CI_EMS_START = 4, CI_EMS_N = 5, CI_GUIDE_START = 10,
+       CI_HAS_GUIDE = 11 };
 enum { RI_NODE = 0, RI_EVENT = 1, RI_HAS_FACET = 2, RI_HIST_START = 3, RI_HIST_N = 4 };
 enum { HI_PROP_A = 0, HI_PROP_B = 1, HI_NA = 2, HI_NB = 3, HI_OFFSET = 4 };
 enum { LI_POS = 0, LI_DIR = 1, LI_WL = 2, LI_WL_START = 3, LI_WL_N = 4 };
