@@ -145,7 +145,7 @@ __host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 115
 // carries nothing it does not need.
 __host__ __device__ constexpr size_t pool_bytes(int P) {
   return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/ + 1 /*tallied*/) +
-         (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/;
+         (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/ + 128 /*decoy words of atoms_add_by*/;
 }
 __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
   return 16 + (size_t)blob_words * 8 + pool_bytes(P);
@@ -246,27 +246,31 @@ __device__ __forceinline__ uint32_t atoms_add(uint32_t* p, uint32_t v) {
   return old;
 }
 
+// One elected lane adds `v` to a shared counter and every lane gets the old value -- executed by ALL 32 lanes: the
+// others add zero to a decoy word of their own (counters + 32 + lane).  ptxas wraps its own warp aggregation (vote,
+// find-leader, popc, predicate, shuffle, add: a dozen dependent instructions) around any shared add whose address is
+// the same in every lane, inline PTX included; with an address that differs per lane it emits the single ATOMS.
+__device__ __forceinline__ uint32_t atoms_add_by(int leader, int lane, uint32_t* counters, int word, uint32_t v) {
+  const bool mine = lane == leader;
+  const uint32_t old = atoms_add(counters + (mine ? word : 32 + lane), mine ? v : 0u);
+  return __shfl_sync(kFullMask, old, leader);
+}
+
 // The VOLUME and SURFACE queue lengths share one 32-bit word (VOLUME | SURFACE << 16; the EXIT queue has its own), so
 // a classified chunk appends to the queues with one or two independent shared atomics.  (A 64-bit word for all three
 // would be a compare-and-swap loop: there is no native 64-bit shared-memory add.)
-__device__ __forceinline__ void push_queues(const uint16_t* qv_, const uint16_t* qs_, const uint16_t* qe_, uint32_t* lengths,
-                                            int cls, int s, int lane) {
+__device__ __forceinline__ void push_queues(const uint16_t* qv_, const uint16_t* qs_, const uint16_t* qe_, uint32_t* counters,
+                                            int word, int cls, int s, int lane) {
   uint16_t* qv = const_cast<uint16_t*>(qv_); uint16_t* qs = const_cast<uint16_t*>(qs_); uint16_t* qe = const_cast<uint16_t*>(qe_);
   const unsigned mv = __ballot_sync(kFullMask, cls == kVolume), ms = __ballot_sync(kFullMask, cls == kSurface),
                  me = __ballot_sync(kFullMask, cls == kExit || cls == kKill);
   uint32_t base_vs = 0, base_e = 0;
-  if (lane == 0) {
-    if (mv | ms) base_vs = atoms_add(lengths, (uint32_t)__popc(mv) | ((uint32_t)__popc(ms) << 16));
-    if (me) base_e = atoms_add(lengths + 1, (uint32_t)__popc(me));
-  }
-  base_vs = __shfl_sync(kFullMask, base_vs, 0);
+  if (mv | ms) base_vs = atoms_add_by(0, lane, counters, word, (uint32_t)__popc(mv) | ((uint32_t)__popc(ms) << 16));
+  if (me) base_e = atoms_add_by(0, lane, counters, word + 1, (uint32_t)__popc(me));
   const unsigned below = (1u << lane) - 1u;
   if (cls == kVolume) qv[(base_vs & 0xffffu) + __popc(mv & below)] = (uint16_t)s;
   else if (cls == kSurface) qs[(base_vs >> 16) + __popc(ms & below)] = (uint16_t)s;
-  if (me) {
-    base_e = __shfl_sync(kFullMask, base_e, 0);
-    if (cls == kExit || cls == kKill) qe[base_e + __popc(me & below)] = (uint16_t)s;
-  }
+  if (cls == kExit || cls == kKill) qe[base_e + __popc(me & below)] = (uint16_t)s;
 }
 
 // initial state of photon i of the bundle (global arrays or the emitter); out of line: the common path takes
@@ -316,10 +320,8 @@ __device__ __forceinline__ void extend_sequence(const TraceArgs& a, uint32_t* co
 }
 
 // take the next chunk of 32 work items of the current stage: one shared atomic per warp
-__device__ __forceinline__ uint32_t steal_chunk(uint32_t* counter, int lane) {
-  uint32_t c = 0;
-  if (lane == 0) c = atoms_add(counter, 1u);
-  return __shfl_sync(kFullMask, c, 0);
+__device__ __forceinline__ uint32_t steal_chunk(uint32_t* counters, int word, int lane) {
+  return atoms_add_by(0, lane, counters, word, 1u);
 }
 
 // ---- service warps --------------------------------------------------------------------------------------------
@@ -404,7 +406,7 @@ __device__ __forceinline__ void service_loop(const TraceArgs& a, const SceneView
     const uint32_t ray_chunks = (ray_hi - ray_lo + 31u) >> 5;
     const double* half = ring + (size_t)(batch & 1u) * kReqWords * P;  // batch b = requests of iteration b - 2
     for (;;) {
-      uint32_t chunk = steal_chunk(pool.counters + kSvcSteal, lane);
+      uint32_t chunk = steal_chunk(pool.counters, kSvcSteal, lane);
       if (chunk >= ray_chunks + chunks) break;
       if (chunk < ray_chunks) {  // fresh rays first: the tracing warps refill from them next iteration
         const uint32_t o = ray_lo + chunk * 32u + (uint32_t)lane;
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         pool.counters[kCtrSteal + 1] = 0u;  // stage 2's work counter
       }
       for (;;) {
-        uint32_t chunk = steal_chunk(pool.counters + kCtrSteal, lane);
+        uint32_t chunk = steal_chunk(pool.counters, kCtrSteal, lane);
         if (chunk >= classify_chunks + ray_chunks) break;
         // Ray production first: its loads have the longest latency of the stage (HBM, or host memory over PCIe
         // when the caller's arrays are page-locked) and the warp that waits for them simply takes fewer
@@ -577,17 +579,13 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
           const unsigned m = __ballot_sync(kFullMask, dead);
           bool fresh = false;
           if (m) {
-            uint32_t base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) {
-              // take popc(m) ray indices, but none at or beyond `avail`: what was taken in excess is given back
-              // (another warp may see the inflated cursor meanwhile and take less than it could -- its slots
-              // simply stay empty until the next iteration; indices below `avail` are handed out exactly once)
-              const uint32_t cnt = (uint32_t)__popc(m);
-              base = atoms_add(pool.counters + kCtrNext, cnt);
-              if (base + cnt > avail) atoms_add(pool.counters + kCtrNext, 0u - (base + cnt - (base > avail ? base : avail)));
-            }
-            base = __shfl_sync(kFullMask, base, leader);
+            // take popc(m) ray indices, but none at or beyond `avail`: what was taken in excess is given back
+            // (another warp may see the inflated cursor meanwhile and take less than it could -- its slots
+            // simply stay empty until the next iteration; indices below `avail` are handed out exactly once)
+            const uint32_t cnt = (uint32_t)__popc(m);
+            const uint32_t base = atoms_add_by(0, lane, pool.counters, kCtrNext, cnt);
+            if (lane == 0 && base + cnt > avail)
+              atoms_add(pool.counters + kCtrNext, 0u - (base + cnt - (base > avail ? base : avail)));
             const uint32_t mine = base + __popc(m & ((1u << lane) - 1u));
             if (dead && mine < avail) {
               const long long i = sequence_photon(pool.counters, mine);
@@ -631,7 +629,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
               live = true;
             }
           }
-          push_queues(pool.qv, pool.qs, pool.qe, qn, cls, slot, lane);
+          push_queues(pool.qv, pool.qs, pool.qe, pool.counters, 4 * (int)(iter & 1), cls, slot, lane);
         }
       }
     }
@@ -657,7 +655,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
       pool.counters[kCtrSteal] = 0u;  // stage 1's work counter
     }
     for (;;) {
-      uint32_t chunk = steal_chunk(pool.counters + kCtrSteal + 1, lane);
+      uint32_t chunk = steal_chunk(pool.counters, kCtrSteal + 1, lane);
       if (chunk >= nv + ns + ne) break;
       int slot = -1, cls;
       if (chunk < nv) {
