@@ -1,5 +1,6 @@
+"""Host-ray end to end: PVT_DEBUG_TIMING=1 python tools/e2e_upload_timing.py prints when the upload and the trace ended."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pvtrace_b200 as pv
 from pvtrace_b200.device import configs
@@ -15,10 +16,10 @@ ctx.emit(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), n, seed=1)
 for a, b in zip(h, d): a.copy_(b)
 torch.cuda.synchronize()
 arrs = [t.numpy() for t in h]
-for mc, sh in ((65536, 5), (131072, 5), (131072, 4), (262144, 4), (262144, 3), (524288, 3), (32768, 6)):
-    os.environ["PVT_UPLOAD_MIN_CHUNK"] = str(mc); os.environ["PVT_UPLOAD_SHRINK"] = str(sh)
-    best = 1e9
-    for rep in range(4):
+for chunks in (8, 16, 32, 48):
+    os.environ["PVT_UPLOAD_CHUNKS"] = str(chunks)
+    for rep in range(3):
+        t0 = time.perf_counter()
         out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
-        best = min(best, el)
-    print(f"min_chunk={mc} shrink=1/{sh}: device-elapsed best {best*1e3:.2f} ms", flush=True)
+        dt = time.perf_counter() - t0
+    print(f"chunks={chunks:2d}: wall {dt*1e3:.2f} ms  device-elapsed {el*1e3:.2f} ms", flush=True)
