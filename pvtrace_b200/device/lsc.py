@@ -180,3 +180,103 @@ class LSC(object):
         out.update(lost=rec["lost"].rays, exit=rec["exit"].rays, killed=rec["killed"].rays,
                    thrown=self._result.num_rays)
         return out
+
+    # -- report (lsc.py:379-607 rebuilt on the engine's event log instead of per-ray pandas rows) ----------------
+
+    def _end_rays(self):
+        """Entrance and exit rows of every logged ray, as the reference stores them (lsc.py:338-364): the entrance is
+        the first event after GENERATE; the exit is the last event of a ray that was lost or killed, the event before
+        EXIT otherwise (where the ray left the LSC region).  Returns a dict of equally long arrays:
+        kind ('entrance' | 'exit'), event (lower-case name), facet (name or None), luminescent (bool: the ray's
+        source is a component, not a light), wavelength.
+
+        Two deliberate differences from the reference's code, which is older than its own tracer: rays whose last
+        event is NONRADIATIVE or REACT count as lost (the reference only tests for ABSORB, which is never last any
+        more), and facets are named by their outward normal as the solar-cell delegate names them (lsc.py:38-47:
+        near = -y, far = +y; `label_facets`, lsc.py:447-452, has the two swapped)."""
+        from pvtrace_b200.light.event import Event
+
+        result = self._result
+        if result is None:
+            raise ValueError("Run a simulation before calling this method.")
+        if result.num_recorded == 0:
+            raise ValueError("The report is built from logged histories: simulate(..., record_every=k) with k >= 1.")
+        d, m = result.data, result.max_events
+        counts = np.asarray(d["counts"], dtype=np.int64)
+        base = np.arange(len(counts), dtype=np.int64) * m
+        has_entrance = counts > 1
+        last = base + counts - 1
+        last_kind = d["kind"][last]
+        lost = np.isin(last_kind, [Event.ABSORB.value, Event.NONRADIATIVE.value, Event.REACT.value, Event.KILL.value])
+        left = (last_kind == Event.EXIT.value) & (counts > 1)
+        rows = np.concatenate([(base + 1)[has_entrance], last[lost], (last - 1)[left]])
+        kinds = np.array(["entrance"] * int(has_entrance.sum()) + ["exit"] * int(lost.sum() + left.sum()))
+        position = d["position"][rows]
+        half = 0.5 * np.asarray(self.size, dtype=float)
+        facet = np.full(len(rows), None, dtype=object)
+        for name, normal in FACES.items():  # later names win, like the reference's successive .loc assignments
+            axis = int(np.argmax(np.abs(normal)))
+            on = np.isclose(position[:, axis], normal[axis] * half[axis], atol=2.220446049250313e-13)
+            facet[on] = name
+        names = {e.value: e.name.lower() for e in Event}
+        return {"kind": kinds, "event": np.array([names[int(k)] for k in d["kind"][rows]]), "facet": facet,
+                "luminescent": d["source"][rows] >= 0, "wavelength": d["wavelength"][rows]}
+
+    def spectrum(self, facets=(), kind="last", source="all", events=None):
+        """Wavelengths of the stored end rays (lsc.py:508-575): kind 'first' (entrance) | 'last' (exit) | None,
+        source 'all' | 'light' | 'luminescent', facets a collection of face names (empty: any), events a collection of
+        lower-case event names (None: any)."""
+        if kind not in (None, "first", "last"):
+            raise ValueError("Direction must be either `'first'` or `'last'.`")
+        if source not in ("all", "light", "luminescent"):
+            raise ValueError("Unknown source requested.", source)
+        rows = self._end_rays()
+        keep = np.ones(len(rows["kind"]), dtype=bool)
+        if kind is not None:
+            keep &= rows["kind"] == ("entrance" if kind == "first" else "exit")
+        if source != "all":
+            keep &= rows["luminescent"] == (source == "luminescent")
+        if len(facets) > 0:
+            keep &= np.isin(rows["facet"].astype(str), list(facets))
+        if events is not None:
+            keep &= np.isin(rows["event"], list(events))
+        return rows["wavelength"][keep]
+
+    def counts_table(self):
+        """{column: {facet: count}} with the reference's four columns (lsc.py:455-506)."""
+        table = {}
+        for column, source, kind in (("Solar In", "light", "first"), ("Solar Out", "light", "last"),
+                                     ("Luminescent Out", "luminescent", "last"), ("Luminescent In", "luminescent", "first")):
+            table[column] = {face: int(len(self.spectrum(facets={face}, source=source, kind=kind)))
+                             for face in ("left", "right", "near", "far", "top", "bottom")}
+        return table
+
+    def summary(self):
+        """Efficiencies of the run (lsc.py:577-607), over the logged rays."""
+        table = self.counts_table()
+        faces = set(FACES)
+        collected = sum(table["Luminescent Out"][f] for f in self._solar_cell_surfaces)
+        escaped = sum(table["Luminescent Out"][f] for f in faces - self._solar_cell_surfaces)
+        incident = sum(table["Solar In"][f] for f in faces)
+        lost = int(len(self.spectrum(kind="last", events={"absorb", "nonradiative", "react"})))
+        (l, w, d) = self.size
+        geometric = (w * l) / (2 * l * d + 2 * w * d)
+        n = self.n1
+        return {"Optical Efficiency": collected / incident if incident else float("nan"),
+                "Waveguide Efficiency": collected / (collected + escaped) if collected + escaped else float("nan"),
+                "Waveguide Efficiency (Thermodynamic Prediction)": n ** 2 / (geometric + n ** 2),
+                "Non-radiative Loss (fraction):": lost / incident if incident else float("nan"),
+                "Incident": incident, "Geometric Concentration": geometric, "Refractive Index": n,
+                "Cell Surfaces": set(self._solar_cell_surfaces), "Components": self.component_names(),
+                "Lights": self.light_names()}
+
+    def report(self):
+        print("\nSimulation Report\n-----------------\n\nSurface Counts:")
+        table = self.counts_table()
+        columns = list(table)
+        print("        " + "  ".join(f"{c:>15s}" for c in columns))
+        for face in ("left", "right", "near", "far", "top", "bottom"):
+            print(f"{face:8s}" + "  ".join(f"{table[c][face]:15d}" for c in columns))
+        print("\nSummary:")
+        for key, value in self.summary().items():
+            print(f"{key:50s} {value}")
