@@ -436,3 +436,29 @@ def test_event_logs_do_not_depend_on_who_tallies_or_on_the_drain(gpu, monkeypatc
                 np.testing.assert_allclose(other[key], base[key], rtol=1e-12, atol=1e-12, err_msg=f"{n} {mode} {key}")
             for key in ("rec_distinct", "rec_crossings", "rec_bins"):
                 assert (other[key] == base[key]).all(), (n, mode, key)
+
+
+def test_lsc_report_on_device_histories(gpu):
+    """LSC.simulate + counts_table / summary (device/lsc.py) on the device's own event log: the table adds up, the
+    back mirror and the edge cells show, and the sampled report agrees with the all-ray recorders within 5 sigma."""
+    from pvtrace_b200.device.lsc import LSC
+
+    lsc = LSC((5.0, 5.0, 1.0))
+    lsc.add_solar_cell({"left", "right", "near", "far"})
+    lsc.add_back_surface_mirror()
+    n, every = 40000, 4
+    result = lsc.simulate(n, seed=12, record_every=every, max_events=512)
+    table, summary = lsc.counts_table(), lsc.summary()
+    sampled = result.num_recorded
+    assert sampled == n // every and summary["Incident"] == sampled == table["Solar In"]["top"]
+    assert table["Luminescent Out"]["bottom"] == 0 and table["Solar Out"]["bottom"] == 0
+    out = sum(table["Luminescent Out"].values()) + sum(table["Solar Out"].values())
+    lost = round(summary["Non-radiative Loss (fraction):"] * sampled)
+    killed = len(lsc.spectrum(kind="last", events={"kill"}))
+    assert out + lost + killed == sampled
+    counts = lsc.counts()  # recorders: every ray
+    for face in ("left", "right", "near", "far", "top"):
+        p = (counts["escaping"][face] + counts["reflected"][face]) / n  # left through the face, or bounced off it
+        seen = table["Luminescent Out"][face] + table["Solar Out"][face]
+        assert abs(seen - p * sampled) <= 5 * np.sqrt(sampled * p * (1 - p)) + 3, face
+    assert 0.3 < summary["Optical Efficiency"] < 0.6
