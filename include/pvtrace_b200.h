@@ -167,7 +167,11 @@ typedef struct pvt_params_t {
 /* Kernel selection.  By default a bundle is traced by the shared-memory wavefront kernel whenever the scene
  * allows it (Philox stream, <= 64 recorders, tables + photon pool fit in shared memory) and by the
  * one-photon-per-lane register kernel otherwise; this flag forces the latter (tests cross-check the two). */
-enum { PVT_FLAG_REGISTER_KERNEL = 1 };
+enum {
+  PVT_FLAG_REGISTER_KERNEL = 1, /* trace_kernel: one photon per lane in registers                                */
+  PVT_FLAG_WARP_KERNEL = 2,     /* warp_wavefront_kernel: autonomous warps, each with its own pool and queues       */
+  PVT_FLAG_CTA_KERNEL = 4       /* wavefront_kernel: two-stage CTA wavefront with service warps                     */
+};
 
 /* Run statistics written by every trace (device counters, not estimates). */
 enum {
@@ -175,7 +179,7 @@ enum {
   PVT_STAT_RAYS = 1,       /* rays retired                                                               */
   PVT_STAT_LAUNCHES = 2,   /* kernels launched by the call                                               */
   PVT_STAT_EVENTS = 3,     /* events generated (logged or not)                                           */
-  PVT_NSTATS = 8
+  PVT_NSTATS = 32
 };
 
 /* Outputs of one bundle: exactly the dict returned by the reference's trace_bundle (_kernel.pyx:1097-1115).

@@ -43,11 +43,20 @@ static const double C_CM_PER_S = 2.99792458e10;
 /* ------------------------------------------------------------------------------------------------
  * Random streams.
  *   XOSHIRO: splitmix64-seeded xoshiro256+, _kernel.pyx:82-113, state seeded with (seed + i) (:1090).
- *   PHILOX : Philox4x32-10 (Salmon et al., SC'11), fixed key, counter = (ray id lo, ray id hi, block, stream);
- *            one block yields two 53-bit uniforms.  Shared definition with pvtrace_b200/csrc/pvt_rng.cuh.   */
+ *   PHILOX : Philox4x32-10 (Salmon et al., SC'11), fixed key, counter = (id lo, id hi, block, stream) with
+ *            id = hash(seed) + first_index + i (splitmix64 finaliser: every seed owns its own window of the
+ *            counter space); one block yields two 53-bit uniforms.  Shared definition with
+ *            pvtrace_b200/csrc/pvt_rng.cuh.                                                                  */
 
 #define PHILOX_KEY0 0x50565442u /* "PVTB" */
 #define PHILOX_KEY1 0x32303042u /* "200B" */
+
+static uint64_t hash_seed(uint64_t seed) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
 
 static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   for (int round = 0; round < 10; ++round) {
@@ -68,8 +77,9 @@ static inline double u53(uint32_t lo, uint32_t hi) {
   return (double)(v >> 11) * (1.0 / 9007199254740992.0);
 }
 
-/* draw number `k` (0-based) of stream `stream` of ray `id` -- random access */
-static double philox_uniform_at(uint64_t id, uint32_t stream, uint32_t k) {
+/* draw number `k` (0-based) of stream `stream` of photon `index` of the run seeded `seed` -- random access */
+static double philox_uniform_at(uint64_t seed, uint64_t index, uint32_t stream, uint32_t k) {
+  uint64_t id = hash_seed(seed) + index;
   uint32_t c[4] = {(uint32_t)id, (uint32_t)(id >> 32), k >> 1, stream};
   philox4x32_10(c, PHILOX_KEY0, PHILOX_KEY1);
   return (k & 1u) ? u53(c[2], c[3]) : u53(c[0], c[1]);
@@ -78,14 +88,15 @@ static double philox_uniform_at(uint64_t id, uint32_t stream, uint32_t k) {
 typedef struct {
   int mode;
   uint64_t s[4]; /* xoshiro state */
-  uint64_t id;   /* philox: ray id */
+  uint64_t id;   /* philox: photon index within the run */
+  uint64_t seed; /* philox: key */
   uint32_t k;    /* philox: sequential cursor of rng_next() (known-answer helpers only) */
   uint32_t step; /* philox: trace-loop iteration the addressed draws belong to */
 } rng_t;
 
 /* Draw addressing of the tracer in PHILOX mode (shared definition with pvtrace_b200/csrc/pvt_rng.cuh): every
- * random decision of a photon step has the fixed address (ray id, step, block, half) -> Philox counter
- * (id_lo, id_hi, step * 8 + block, stream 0), half selecting the first or second 53-bit uniform of the block.
+ * random decision of a photon step has the fixed address (photon index, step, block, half) -> Philox counter
+ * (index_lo, index_hi, step * 8 + block, stream 0), half selecting the first or second 53-bit uniform of the block.
  * In XOSHIRO mode addresses are ignored and draws are consumed in program order, which is the reference's. */
 enum { BLOCK_PATH = 0, BLOCK_ABSORB = 1, BLOCK_PHASE = 2, BLOCK_EMIT = 3, BLOCK_LAMBERT = 4, BLOCKS_PER_STEP = 8 };
 
@@ -96,12 +107,13 @@ static uint64_t splitmix64(uint64_t* x) {
   return z ^ (z >> 31);
 }
 
-static void rng_init(rng_t* r, int mode, uint64_t id) {
+static void rng_init(rng_t* r, int mode, uint64_t seed, uint64_t index) {
   r->mode = mode;
-  r->id = id;
+  r->id = index;
+  r->seed = seed;
   r->k = 0;
   r->step = 0;
-  uint64_t x = id;
+  uint64_t x = seed + index; /* the reference's per-ray seed, _kernel.pyx:1090 */
   for (int i = 0; i < 4; ++i) r->s[i] = splitmix64(&x);
 }
 
@@ -118,12 +130,12 @@ static double rng_next(rng_t* r) {
     s[3] = (s[3] << 45) | (s[3] >> 19);
     return (double)(result >> 11) * (1.0 / 9007199254740992.0);
   }
-  return philox_uniform_at(r->id, 0u, r->k++);
+  return philox_uniform_at(r->seed, r->id, 0u, r->k++);
 }
 
 static double rng_draw(rng_t* r, uint32_t block, uint32_t half) {
   if (r->mode == PVT_RNG_XOSHIRO) return rng_next(r);
-  return philox_uniform_at(r->id, 0u, ((r->step * BLOCKS_PER_STEP + block) << 1) | half);
+  return philox_uniform_at(r->seed, r->id, 0u, ((r->step * BLOCKS_PER_STEP + block) << 1) | half);
 }
 
 /* ------------------------------------------------------------------------------------------------
@@ -468,9 +480,9 @@ static void lambert_about(const double* n, double p1, double p2, double* out) {
 }
 
 static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, acc_t* A, double* pos, double* dir,
-                        double wl, uint64_t ray_id, int64_t* steps_out) {
+                        double wl, uint64_t index, int64_t* steps_out) {
   rng_t rng;
-  rng_init(&rng, P->rng_mode, ray_id);
+  rng_init(&rng, P->rng_mode, P->seed, index);
   unsigned char seen[PVT_MAX_RECORDERS];
   memset(seen, 0, (size_t)(S->n_recorders > 0 ? S->n_recorders : 1));
   double travelled = 0.0, duration = 0.0;
@@ -657,13 +669,14 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
 
 /* ------------------------------------------------------------------------------------------------
  * Seeded emission of built-in light delegates (emit.py:22-134; scene.py:141-151 for the round robin).
- * Draw k of Philox stream 1 of ray id: k=0 wavelength, k=1..3 position, k=4,5 direction.               */
+ * Draw k of Philox stream 1 of photon `index` under key `seed`: k=0 wavelength, k=1..3 position, k=4,5 direction.               */
 
-static void emit_one(const pvt_emit_t* E, uint64_t id, int64_t index, double* pos, double* dir, double* wl) {
+static void emit_one(const pvt_emit_t* E, uint64_t seed, int64_t index, double* pos, double* dir, double* wl) {
+  const uint64_t id = (uint64_t)index;
   int l = (int)(index % E->n_lights);
   double lp[3] = {0.0, 0.0, 0.0}, ld[3] = {0.0, 0.0, 1.0};
   if (E->wl_kind[l] == PVT_LWL_SPECTRUM) {
-    double u = philox_uniform_at(id, 1u, 0u);
+    double u = philox_uniform_at(seed, id, 1u, 0u);
     *wl = interp_clamped(u, E->wl_cdf + E->wl_start[l], E->wl_x + E->wl_start[l], E->wl_n[l]);
   } else {
     *wl = E->wl_param[l];
@@ -671,20 +684,20 @@ static void emit_one(const pvt_emit_t* E, uint64_t id, int64_t index, double* po
   const double* pp = E->pos_param + 3 * l;
   switch (E->pos_kind[l]) {
     case PVT_LPOS_RECT:
-      lp[0] = -pp[0] + (pp[0] - -pp[0]) * philox_uniform_at(id, 1u, 1u);
-      lp[1] = -pp[1] + (pp[1] - -pp[1]) * philox_uniform_at(id, 1u, 2u);
+      lp[0] = -pp[0] + (pp[0] - -pp[0]) * philox_uniform_at(seed, id, 1u, 1u);
+      lp[1] = -pp[1] + (pp[1] - -pp[1]) * philox_uniform_at(seed, id, 1u, 2u);
       break;
     case PVT_LPOS_CIRCLE: {
-      double ang = 2.0 * M_PI * philox_uniform_at(id, 1u, 1u);
-      double r = sqrt(philox_uniform_at(id, 1u, 2u)) * pp[0];
+      double ang = 2.0 * M_PI * philox_uniform_at(seed, id, 1u, 1u);
+      double r = sqrt(philox_uniform_at(seed, id, 1u, 2u)) * pp[0];
       lp[0] = r * cos(ang); lp[1] = r * sin(ang);
     } break;
     case PVT_LPOS_CUBE:
-      for (int i = 0; i < 3; ++i) lp[i] = -pp[i] + (pp[i] - -pp[i]) * philox_uniform_at(id, 1u, 1u + i);
+      for (int i = 0; i < 3; ++i) lp[i] = -pp[i] + (pp[i] - -pp[i]) * philox_uniform_at(seed, id, 1u, 1u + i);
       break;
     default: break;
   }
-  double u0 = philox_uniform_at(id, 1u, 4u), u1 = philox_uniform_at(id, 1u, 5u);
+  double u0 = philox_uniform_at(seed, id, 1u, 4u), u1 = philox_uniform_at(seed, id, 1u, 5u);
   double prm = E->dir_param[l];
   int kind = E->dir_kind[l];
   if (kind == PVT_LDIR_HG && fabs(prm) < 1e-12) kind = PVT_LDIR_ISOTROPIC;
@@ -712,7 +725,7 @@ int pvt_oracle_emit_bundle(const pvt_emit_t* E, double* pos, double* dir, double
   if (!E || E->n_lights <= 0) return 1;
 #pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i)
-    emit_one(E, seed + (uint64_t)first_index + (uint64_t)i, first_index + i, pos + 3 * i, dir + 3 * i, wl + i);
+    emit_one(E, seed, first_index + i, pos + 3 * i, dir + 3 * i, wl + i);
   return 0;
 }
 
@@ -745,13 +758,13 @@ int pvt_oracle_trace_bundle(const pvt_scene_t* S, const pvt_emit_t* E, const dou
                t_bins + (size_t)tid * B};
     log_t L = {out, -1, P->max_events, 0};
     if (P->record_every > 0 && i % P->record_every == 0) L.base = (i / P->record_every) * (int64_t)P->max_events;
-    uint64_t id = P->seed + (uint64_t)P->first_index + (uint64_t)i;
+    uint64_t id = (uint64_t)P->first_index + (uint64_t)i; /* photon index within the run */
     double pos[3], dir[3], wl;
     if (positions) {
       for (int k = 0; k < 3; ++k) { pos[k] = positions[3 * i + k]; dir[k] = directions[3 * i + k]; }
       wl = wavelengths[i];
     } else {
-      emit_one(E, id, P->first_index + i, pos, dir, &wl);
+      emit_one(E, P->seed, P->first_index + i, pos, dir, &wl);
     }
     int64_t steps = 0;
     int nev = trace_photon(S, P, &L, &A, pos, dir, wl, id, &steps);
@@ -835,7 +848,7 @@ int pvt_oracle_rng_uniform(int64_t n_rays, int32_t n_draws, uint64_t seed, int64
                            double* out) {
   for (int64_t i = 0; i < n_rays; ++i) {
     rng_t r;
-    rng_init(&r, rng_mode, seed + (uint64_t)first_index + (uint64_t)i);
+    rng_init(&r, rng_mode, seed, (uint64_t)first_index + (uint64_t)i);
     for (int k = 0; k < n_draws; ++k) out[i * n_draws + k] = rng_next(&r);
   }
   return 0;
@@ -844,7 +857,7 @@ int pvt_oracle_sample_phase(int64_t n, int32_t phase_type, double phase_param, u
                             double* out) {
   for (int64_t i = 0; i < n; ++i) {
     rng_t r;
-    rng_init(&r, rng_mode, seed + (uint64_t)i);
+    rng_init(&r, rng_mode, seed, (uint64_t)i);
     double g1 = rng_next(&r), g2 = rng_next(&r);
     phase_dir(phase_type, phase_param, g1, g2, out + 3 * i);
   }

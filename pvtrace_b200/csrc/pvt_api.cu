@@ -12,7 +12,8 @@
 
 #include "../../include/pvtrace_b200.h"
 #include "pvt_common.cuh"
-#include "pvt_kernels.cuh"
+#include "pvt_aux_kernels.cuh"
+#include "pvt_launch.h"
 
 namespace pvt {
 
@@ -57,6 +58,9 @@ struct pvt_context {
   int wave_ctas = 1;        // resident CTAs per SM
   bool wave_boxes = false;  // every node is an axis-aligned box: the kBoxes instantiation (no primitive switch)
   size_t wave_smem = 0;
+  // warp_wavefront_kernel (autonomous warps): shape chosen for the scene, 0 warps: does not fit
+  int wave2_warps = 0, wave2_slots = 0;
+  bool prefer_wave2 = false;
   // event log of the last trace
   long long log_rows = 0, log_rays = 0;
   DeviceBuffer<int32_t> counts, hit, container, adjacent, component, source;
@@ -105,81 +109,6 @@ static int validate_scene(const pvt_scene_t* S) {
   return 0;
 }
 
-template <class K>
-static int occupancy(K kernel, size_t smem, int* blocks) {
-  if (smem > 48 * 1024)
-    PVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PVT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, kernel, kTraceThreads, smem));
-  if (*blocks < 1) return fail("trace kernel cannot be resident with %zu bytes of shared memory", smem);
-  return 0;
-}
-
-// (threads, pool slots, resident CTAs per SM), preferred first; the first that fits the scene's shared memory wins
-struct WaveVariant { int threads, pool, ctas; };
-#ifdef PVT_SWEEP  // extra shapes for tools/sweep.sh experiments (selected with PVT_WAVEFRONT_* in the environment)
-constexpr int kWaveVariants = 11;
-#else
-constexpr int kWaveVariants = 7;
-#endif
-static const WaveVariant kWaveTable[kWaveVariants] = {{512, 1024, 1}, {480, 960, 1}, {448, 896, 1}, {512, 768, 1},
-                                                      {512, 512, 1},  {384, 768, 1}, {256, 512, 1},
-#ifdef PVT_SWEEP
-                                                      {256, 512, 2}, {640, 1280, 1}, {768, 768, 1}, {1024, 1024, 1},
-#endif
-};
-
-template <class K>
-static int wave_attr(K kernel, size_t smem) {
-  PVT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  return 0;
-}
-
-// launches (or, with args == nullptr, only configures) the wavefront variant chosen for the context
-#define PVT_WAVE_CASE(T, P, B)                                                                   \
-  if (c->wave_threads == T && c->wave_pool == P && c->wave_ctas == B) {                          \
-    if (!args) {                                                                                 \
-      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, false>, c->wave_smem));                 \
-      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, true>, c->wave_smem));                  \
-      PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, false>, c->wave_smem));                  \
-      if (T == 512 && P == 1024 && B == 1) {                                                     \
-        constexpr int TS = (T == 512 && P == 1024 && B == 1) ? 128 : 0;                          \
-        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, false, TS>, c->wave_smem));           \
-        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, false, true, TS>, c->wave_smem));            \
-        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, false, TS>, c->wave_smem));            \
-        PVT_TRY(wave_attr(wavefront_kernel<T, P, B, true, true, TS>, c->wave_smem));             \
-      }                                                                                          \
-      return wave_attr(wavefront_kernel<T, P, B, true, true>, c->wave_smem);                     \
-    }                                                                                            \
-    const bool log = args->record_every > 0;                                                     \
-    if (T == 512 && P == 1024 && B == 1 && c->wave_service > 0) {                                \
-      constexpr int TS = (T == 512 && P == 1024 && B == 1) ? 128 : 0;                            \
-      if (c->wave_boxes) {                                                                       \
-        if (log) wavefront_kernel<T, P, B, true, true, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);    \
-        else wavefront_kernel<T, P, B, false, true, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);       \
-      } else {                                                                                   \
-        if (log) wavefront_kernel<T, P, B, true, false, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);   \
-        else wavefront_kernel<T, P, B, false, false, TS><<<grid, T + TS, c->wave_smem, st>>>(*args);      \
-      }                                                                                          \
-      return 0;                                                                                  \
-    }                                                                                            \
-    if (c->wave_boxes) {                                                                         \
-      if (log) wavefront_kernel<T, P, B, true, true><<<grid, T, c->wave_smem, st>>>(*args);      \
-      else wavefront_kernel<T, P, B, false, true><<<grid, T, c->wave_smem, st>>>(*args);         \
-    } else {                                                                                     \
-      if (log) wavefront_kernel<T, P, B, true, false><<<grid, T, c->wave_smem, st>>>(*args);     \
-      else wavefront_kernel<T, P, B, false, false><<<grid, T, c->wave_smem, st>>>(*args);        \
-    }                                                                                            \
-    return 0;                                                                                    \
-  }
-static int launch_wave(pvt_context* c, const TraceArgs* args, int grid, cudaStream_t st) {
-  PVT_WAVE_CASE(512, 1024, 1) PVT_WAVE_CASE(480, 960, 1) PVT_WAVE_CASE(448, 896, 1) PVT_WAVE_CASE(512, 768, 1)
-  PVT_WAVE_CASE(512, 512, 1) PVT_WAVE_CASE(384, 768, 1) PVT_WAVE_CASE(256, 512, 1)
-#ifdef PVT_SWEEP
-  PVT_WAVE_CASE(256, 512, 2) PVT_WAVE_CASE(640, 1280, 1) PVT_WAVE_CASE(768, 768, 1) PVT_WAVE_CASE(1024, 1024, 1)
-#endif
-  return fail("no wavefront kernel variant for %d threads / %d slots x %d CTAs", c->wave_threads, c->wave_pool, c->wave_ctas);
-}
-
 extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context_t** out) {
   if (!out) return fail("ctx out pointer is NULL");
   *out = nullptr;
@@ -218,8 +147,8 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
     if (const char* env = getenv("PVT_WAVEFRONT_THREADS")) want_t = atoi(env);
     if (const char* env = getenv("PVT_WAVEFRONT_POOL")) want_p = atoi(env);
     if (const char* env = getenv("PVT_WAVEFRONT_CTAS")) want_b = atoi(env);
-    for (int k = 0; k < kWaveVariants && want_t >= 0; ++k) {
-      const int t = kWaveTable[k].threads, pl = kWaveTable[k].pool, b = kWaveTable[k].ctas;
+    for (int k = 0; k < wave_variant_count() && want_t >= 0; ++k) {
+      const int t = wave_variant(k).threads, pl = wave_variant(k).pool, b = wave_variant(k).ctas;
       if ((want_t && t != want_t) || (want_p && pl != want_p) || (want_b && b != want_b)) continue;
       size_t need = wavefront_smem_bytes(c->blob_words, pl);
       if (const char* env = getenv("PVT_EXTRA_SMEM")) need += (size_t)atoi(env);  // experiment: shrink L1
@@ -230,6 +159,22 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
     }
   }
 
+  if (c->R() <= 64) {
+    int want_w = 0, want_n = 0;
+    if (const char* env = getenv("PVT_WAVE2_WARPS")) want_w = atoi(env);
+    if (const char* env = getenv("PVT_WAVE2_SLOTS")) want_n = atoi(env);
+    for (int k = 0; k < wave2_variant_count(); ++k) {
+      const Wave2Variant v = wave2_variant(k);
+      if ((want_w && v.warps != want_w) || (want_n && v.slots != want_n)) continue;
+      const size_t need = wave2_smem(v, c->blob_words, true);
+      if (need + 1024 <= (size_t)prop.sharedMemPerMultiprocessor && need <= (size_t)prop.sharedMemPerBlockOptin) {
+        c->wave2_warps = v.warps; c->wave2_slots = v.slots;
+        break;
+      }
+    }
+  }
+  if (const char* env = getenv("PVT_KERNEL")) c->prefer_wave2 = strcmp(env, "wave2") == 0;
+
   int rc = c->blob.reserve((size_t)c->blob_words);
   c->tally_words = (size_t)10 * c->R() + c->B() + PVT_NSTATS + 1;
   if (!rc) rc = c->tallies.reserve(c->tally_words);
@@ -238,17 +183,16 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
   if (!rc) rc = c->slabs.reserve((size_t)c->max_grid * 10 * c->R() + 1);
   if (!rc) rc = c->arrived.reserve(4);
   c->wave_service = (c->wave_threads == 512 && c->wave_pool == 1024 && c->wave_ctas == 1 && c->R() > 0 &&
-                     !(getenv("PVT_TALLY_IN_PLACE") && atoi(getenv("PVT_TALLY_IN_PLACE")))) ? 128 : 0;
+                     !(getenv("PVT_TALLY_IN_PLACE") && atoi(getenv("PVT_TALLY_IN_PLACE")))) ? wave_service_threads() : 0;
   if (!rc && c->wave_service) rc = c->requests.reserve((size_t)c->sm_count * c->wave_ctas * 2 * kReqWords * c->wave_pool);
   if (!rc && cudaMemcpy(c->blob.ptr, c->host_blob.data(), (size_t)c->blob_words * 8, cudaMemcpyHostToDevice) != cudaSuccess)
     rc = fail("scene upload failed: %s", cudaGetErrorString(cudaGetLastError()));
   if (!rc && cudaMemset(c->tallies.ptr, 0, c->tally_words * 8) != cudaSuccess)
     rc = fail("tally reset failed: %s", cudaGetErrorString(cudaGetLastError()));
-  if (!rc) rc = occupancy(trace_kernel<PhiloxStream, 2>, c->smem_bytes, &c->blocks_per_sm[0]);
-  if (!rc) rc = occupancy(trace_kernel<PhiloxStream, 8>, c->smem_bytes, &c->blocks_per_sm[1]);
-  if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 2>, c->smem_bytes, &c->blocks_per_sm[2]);
-  if (!rc) rc = occupancy(trace_kernel<XoshiroStream, 8>, c->smem_bytes, &c->blocks_per_sm[3]);
-  if (!rc && c->wave_threads > 0) rc = launch_wave(c, nullptr, 0, 0);  // attribute setup only
+  for (int which = 0; which < 4 && !rc; ++which) rc = reg_occupancy(which, c->smem_bytes, &c->blocks_per_sm[which]);
+  if (!rc && c->wave_threads > 0) rc = wave_setup(WaveVariant{c->wave_threads, c->wave_pool, c->wave_ctas}, c->wave_smem);
+  if (!rc && c->wave2_warps > 0)
+    rc = wave2_setup(Wave2Variant{c->wave2_warps, c->wave2_slots}, wave2_smem(Wave2Variant{c->wave2_warps, c->wave2_slots}, c->blob_words, true));
   if (!rc && c->smem_bytes > 48 * 1024 &&
       (cudaFuncSetAttribute(intersect_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
        cudaFuncSetAttribute(intersect_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
@@ -341,6 +285,20 @@ static int wave_grid(const pvt_context* c, const pvt_params_t* P) {
   return (int)(want_blocks < resident ? want_blocks : resident);
 }
 
+// does this bundle go through warp_wavefront_kernel?  (same conditions as the CTA wavefront; chosen by PVT_KERNEL=wave2
+// or the PVT_FLAG_WARP_KERNEL bit)
+static bool use_wave2(const pvt_context* c, const pvt_params_t* P) {
+  if (c->wave2_warps <= 0 || P->rng_mode != PVT_RNG_PHILOX || (P->flags & PVT_FLAG_REGISTER_KERNEL) || P->n <= 0) return false;
+  if (P->n >= (1ll << 32) - 1024) return false;
+  if (P->flags & PVT_FLAG_CTA_KERNEL) return false;
+  return c->prefer_wave2 || (P->flags & PVT_FLAG_WARP_KERNEL) || c->wave_threads <= 0;
+}
+static int wave2_grid(const pvt_context* c, const pvt_params_t* P) {
+  const long long per_cta = (long long)c->wave2_warps * c->wave2_slots;
+  const long long want_blocks = (P->n + per_cta - 1) / per_cta;
+  return (int)(want_blocks < c->sm_count ? want_blocks : c->sm_count);
+}
+
 static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
                              const pvt_params_t* P, void* stream, const uint32_t* arrived);
 
@@ -365,7 +323,7 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
   a.hdr = c->hdr;
   a.blob = c->blob.ptr; a.blob_words = c->blob_words; a.scene_in_smem = c->scene_in_smem;
   a.pos = have_rays ? d_pos : nullptr; a.dir = have_rays ? d_dir : nullptr; a.wl = have_rays ? d_wl : nullptr;
-  a.n = P->n; a.first_index = P->first_index; a.record_every = P->record_every; a.seed = P->seed;
+  a.n = P->n; a.first_index = P->first_index; a.record_every = P->record_every; a.keys = make_run_seed(P->seed);
   a.sp.maxsteps = P->maxsteps; a.sp.max_events = P->max_events; a.sp.emit_method = P->emit_method;
   a.work_counter = c->d_work();
   a.g_distinct = c->d_distinct(); a.g_cross = c->d_cross(); a.g_sums = c->d_sums(); a.g_bins = c->d_bins();
@@ -378,10 +336,16 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
   a.requests = c->requests.ptr;
   int grid = wave_grid(c, P);
   a.arrived = arrived;
-  if (grid > 0) {
+  if (use_wave2(c, P)) {
+    grid = wave2_grid(c, P);
+    const Wave2Variant v{c->wave2_warps, c->wave2_slots};
+    PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
+    PVT_TRY(wave2_launch(v, c->wave_boxes, P->record_every > 0, a, grid, wave2_smem(v, c->blob_words, P->record_every > 0), st));
+  } else if (grid > 0) {
     // persistent CTAs that claim blocks of photons from the work counter (zeroed above) as their pools drain
     PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
-    PVT_TRY(launch_wave(c, &a, grid, st));
+    PVT_TRY(wave_launch(WaveVariant{c->wave_threads, c->wave_pool, c->wave_ctas}, c->wave_service, c->wave_boxes,
+                        P->record_every > 0, a, grid, c->wave_smem, st));
   } else {
     if (arrived) return fail("streaming upload needs the wavefront kernel");
     const int wide = c->R() > 64;
@@ -391,12 +355,7 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
     if (resident > c->max_grid) resident = c->max_grid;
     grid = (int)(want_blocks < resident ? want_blocks : resident);
     PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
-    switch (which) {
-      case 0: trace_kernel<PhiloxStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-      case 1: trace_kernel<PhiloxStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-      case 2: trace_kernel<XoshiroStream, 2><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-      default: trace_kernel<XoshiroStream, 8><<<grid, kTraceThreads, c->smem_bytes, st>>>(a); break;
-    }
+    PVT_TRY(reg_launch(which, a, grid, c->smem_bytes, st));
   }
   PVT_CUDA(cudaGetLastError());
   c->launches += 1;
@@ -494,7 +453,7 @@ extern "C" int pvt_emit_device(pvt_context_t* c, double* d_pos, double* d_dir, d
   if (!c->has_emitter) return fail("the context has no emitter");
   if (n <= 0) return 0;
   PVT_CUDA(cudaSetDevice(c->device));
-  emit_kernel<<<grid_for(n, c->sm_count), 256, 0, (cudaStream_t)stream>>>(c->blob.ptr, d_pos, d_dir, d_wl, n, first_index, seed);
+  emit_kernel<<<grid_for(n, c->sm_count), 256, 0, (cudaStream_t)stream>>>(c->blob.ptr, d_pos, d_dir, d_wl, n, first_index, make_run_seed(seed));
   PVT_CUDA(cudaGetLastError());
   return 0;
 }
@@ -637,7 +596,7 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   }
   if (!rc && z_pos) {
     rc = pvt_trace_device(c, z_pos, z_dir, z_wl, params, s_run);
-  } else if (!rc && have_rays && n > 0 && wave_grid(c, params) > 0 && stream_upload_allowed()) {
+  } else if (!rc && have_rays && n > 0 && (wave_grid(c, params) > 0 || use_wave2(c, params)) && stream_upload_allowed()) {
     // Streaming upload: the trace kernel starts at once and polls an arrival mark; the copy engine delivers the
     // arrays front to back in chunks (three plain copies each) followed, in stream order, by the new mark = rays
     // complete so far.  CTAs claim photons in index order, so they consume the prefix as it lands.  Upload and trace
@@ -775,7 +734,7 @@ extern "C" int pvt_emit_bundle(const pvt_emit_t* emit, double* positions, double
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     emit_kernel<<<grid_for(n, prop.multiProcessorCount), 256>>>(d_blob.ptr, d_rays.ptr, d_rays.ptr + 3 * n, d_rays.ptr + 6 * n, n,
-                                                              first_index, seed);
+                                                              first_index, make_run_seed(seed));
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(positions, d_rays.ptr, 24 * (size_t)n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(directions, d_rays.ptr + 3 * n, 24 * (size_t)n, cudaMemcpyDeviceToHost);

@@ -49,7 +49,7 @@ struct TraceArgs {
   const double* dir;
   const double* wl;
   long long n, first_index, record_every;
-  u64 seed;
+  RunSeed keys;  // the run's seed and its window of the Philox counter space
   StepParams sp;
   u64* work_counter;
   u64* slabs;       // [gridDim.x][10 R] CTA-private tally slabs, zero on entry
@@ -128,7 +128,7 @@ __device__ __forceinline__ void retire_cta(const TraceArgs& a, int R, const Lane
 
 // Is ray i of the bundle sampled for the event log, and which recorded ray is it?  (64-bit division: out of line,
 // once per photon.)
-__device__ __noinline__ int sampled_ordinal(long long i, long long record_every) {
+static __device__ __noinline__ int sampled_ordinal(long long i, long long record_every) {
   if (record_every <= 0 || i % record_every != 0) return -1;
   return (int)(i / record_every);
 }
@@ -275,13 +275,13 @@ __device__ __forceinline__ void push_queues(const uint16_t* qv_, const uint16_t*
 
 // initial state of photon i of the bundle (global arrays or the emitter); out of line: the common path takes
 // fresh rays from the shared-memory ring that the spare warps keep filled
-__device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, long long i, V3& p, V3& d, double& wl) {
+static __device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, long long i, V3& p, V3& d, double& wl) {
   if (a.pos) {
     p = V3{__ldcg(a.pos + 3 * i), __ldcg(a.pos + 3 * i + 1), __ldcg(a.pos + 3 * i + 2)};
     d = V3{__ldcg(a.dir + 3 * i), __ldcg(a.dir + 3 * i + 1), __ldcg(a.dir + 3 * i + 2)};
     wl = __ldcg(a.wl + i);
   } else {
-    emit_ray(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i, p, d, wl);
+    emit_ray(sv, a.keys, a.first_index + i, p, d, wl);
   }
 }
 
@@ -340,8 +340,13 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counters, int word, in
 #endif
 constexpr int kDrainPhotons = PVT_DRAIN_PHOTONS;  // a CTA with no supply left and at most this many live photons drains them lane by lane
 constexpr int kReqWords = 8;
-constexpr int kSvcWarps = 4;
-constexpr int kTracerRegs = 104, kSvcRegs = 64;  // 512 x 104 + 128 x 64 = 640 x 96, what the CTA is launched with (the pool is per CTA)
+// Registers after the re-division (the pool is per CTA: the two sides must add up to what the launch allocated):
+//   S = 128: launched as 640 x 96, becomes 512 x 104 + 128 x 64.
+// setmaxnreg is a WARPGROUP instruction (four warps execute it together): a service side of two warps (S = 64, launched
+// as 576 x 112) cannot re-divide -- it hangs -- and keeps the uniform 112.
+__host__ __device__ constexpr bool redivide_regs(int S) { return S > 0 && S % 128 == 0; }
+__host__ __device__ constexpr int tracer_regs(int S) { return 104; }
+__host__ __device__ constexpr int service_regs(int S) { return 64; }
 
 template <int T, int S>
 __device__ __forceinline__ void sync_tracers() {
@@ -384,16 +389,16 @@ __device__ __forceinline__ void produce_ray(const TraceArgs& a, const SceneView&
     r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2);
     r[6 * K] = __ldcg(a.wl + i);
   } else if (kInlineEmitter) {
-    const EmittedRay e = emit_ray_value(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i);
+    const EmittedRay e = emit_ray_value(sv, a.keys, a.first_index + i);
     r[0] = e.pos.x; r[K] = e.pos.y; r[2 * K] = e.pos.z;
     r[3 * K] = e.dir.x; r[4 * K] = e.dir.y; r[5 * K] = e.dir.z;
     r[6 * K] = e.wl;
   } else {
-    emit_ray_to_ring(sv, a.seed + (u64)a.first_index + (u64)i, a.first_index + i, r, K);
+    emit_ray_to_ring(sv, a.keys, a.first_index + i, r, K);
   }
 }
 
-template <int P, int K>
+template <int P, int K, int kSvcWarps>
 __device__ __forceinline__ void service_loop(const TraceArgs& a, const SceneView& sv, const TallySink& sink,
                                              const PoolView& pool, const double* ring, int lane) {
   for (;;) {
@@ -447,6 +452,7 @@ __device__ __forceinline__ void service_loop(const TraceArgs& a, const SceneView
 template <int T, int P, int B, bool kLog, bool kBoxes = false, int S = 0>
 __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_constant__ TraceArgs a) {
   constexpr int K = ring_size(P);
+  constexpr int kSvcWarps = S / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   const PoolView pool = carve_pool(smem_raw + 16 + (size_t)a.blob_words * 8, P);
   const int R = sv.hdr().n_recorders;
   const TallySink sink = cta_sink(a, R);
-  const u64 id0 = a.seed + (u64)a.first_index;
+  const u64 id0 = (u64)a.first_index;  // photon index of ray 0 of the bundle within the run
   const StepParams sp = a.sp;
   const LogColumns& L = a.log;
 
@@ -473,11 +479,11 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   const bool service = S > 0 && tid >= T;
   const bool svc_rays = S > 0;  // the service warps also fill the ring of fresh rays
   if (service) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kSvcRegs));
-    service_loop<P, K>(a, sv, sink, pool, ring, lane);
+    if (redivide_regs(S)) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(service_regs(S)));
+    service_loop<P, K, kSvcWarps>(a, sv, sink, pool, ring, lane);
     __threadfence();
   } else {  // the tracing warps; both roles meet again at retire_cta's barrier below
-  if (S > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTracerRegs));
+  if (redivide_regs(S)) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tracer_regs(S)));
   uint32_t idle_iterations = 0;
   bool draining = false;
 #ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
           if (fresh || !dead) {
             if (!fresh) load_slot_head<kLog>(pool, slot, ph, sp.max_events);
             PhiloxStream rng;
-            rng.id = id0 + (u64)pool.idx[slot];
+            rng.init(a.keys, id0 + (u64)pool.idx[slot]);
             StepPlan plan;
             cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan);
             if (cls == kDead) {
@@ -677,7 +683,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         bool alive = false;
         load_slot<kLog, S == 0>(pool, slot, ph, sp.max_events);
         PhiloxStream rng;
-        rng.id = id0 + (u64)pool.idx[slot];
+        rng.init(a.keys, id0 + (u64)pool.idx[slot]);
         rng.begin_step((uint32_t)ph.count);
         StepPlan plan;
         plan.t = pool.t[slot]; plan.u = pool.u[slot]; plan.alpha = pool.alpha[slot];
@@ -731,7 +737,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
       }
       PhiloxStream rng;
-      rng.id = id0 + (u64)pool.idx[slot];
+      rng.init(a.keys, id0 + (u64)pool.idx[slot]);
       for (;;) {
         StepPlan plan;
         const StepClass cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan);
@@ -828,15 +834,14 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const __grid_const
       }
       if (mine) {
         if (idx >= 0) {
-          const u64 id = a.seed + (u64)a.first_index + (u64)idx;
           if (a.pos) {
             ph.p = V3{a.pos[3 * idx], a.pos[3 * idx + 1], a.pos[3 * idx + 2]};
             ph.d = V3{a.dir[3 * idx], a.dir[3 * idx + 1], a.dir[3 * idx + 2]};
             ph.wl = a.wl[idx];
           } else {
-            emit_ray(sv, id, a.first_index + idx, ph.p, ph.d, ph.wl);
+            emit_ray(sv, a.keys, a.first_index + idx, ph.p, ph.d, ph.wl);
           }
-          rng.init(id);
+          rng.init(a.keys, (u64)a.first_index + (u64)idx);
           ph.log_ray = a.record_every > 0 ? sampled_ordinal(idx, a.record_every) : -1;
           ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * sp.max_events;
           begin_photon<true>(ph, L, sp, st);
@@ -934,105 +939,6 @@ __global__ void __launch_bounds__(256, kMinCtas) intersect_kernel(const __grid_c
       base += stride;
     }
   }
-}
-
-__global__ void __launch_bounds__(256) emit_kernel(const double* blob, double* pos, double* dir, double* wl, long long n,
-                                                   long long first_index, u64 seed) {
-  const SceneView sv{blob};
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    V3 p, d;
-    double w;
-    emit_ray(sv, seed + (u64)first_index + (u64)i, first_index + i, p, d, w);
-    pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z;
-    dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
-    wl[i] = w;
-  }
-}
-
-// tallies <-> packed doubles (the buffer a multi-GPU caller all-reduces)
-__global__ void pack_tallies_kernel(const u64* ints_a, int n_a, const double* sums, int n_s, const u64* bins, int n_b,
-                                    double* packed) {
-  const int total = n_a + n_s + n_b;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    double v;
-    if (k < n_a) v = (double)ints_a[k];
-    else if (k < n_a + n_s) v = sums[k - n_a];
-    else v = (double)bins[k - n_a - n_s];
-    packed[k] = v;
-  }
-}
-__global__ void unpack_tallies_kernel(u64* ints_a, int n_a, double* sums, int n_s, u64* bins, int n_b,
-                                      const double* packed) {
-  const int total = n_a + n_s + n_b;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
-    const double v = packed[k];
-    if (k < n_a) ints_a[k] = (u64)llrint(v);
-    else if (k < n_a + n_s) sums[k - n_a] = v;
-    else bins[k - n_a - n_s] = (u64)llrint(v);
-  }
-}
-
-// ---- known-answer test kernels ----------------------------------------------------------------------------
-
-__global__ void test_fresnel_kernel(long long n, const double* angle, const double* n1, const double* n2, double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = fresnel_R(angle[i], n1[i], n2[i]);
-}
-__global__ void test_reflect_kernel(long long n, const double* d, const double* nrm, double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const V3 r = mirror(V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]}, V3{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]});
-  out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
-}
-__global__ void test_refract_kernel(long long n, const double* d, const double* nrm, const double* n1, const double* n2,
-                                    double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const V3 dd = V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]};
-  V3 nf = V3{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]};
-  if (dot(nf, dd) < 0.0) nf = neg(nf);
-  const V3 r = snell(dd, nf, n1[i], n2[i]);
-  out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
-}
-__global__ void test_intersect_kernel(long long n, const int32_t* gtype, const double* params, const double* o,
-                                      const double* d, int32_t* nhit, double* ts) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  double t[4] = {0.0, 0.0, 0.0, 0.0};
-  const int k = roots(gtype[i], params + 4 * i, V3{o[3 * i], o[3 * i + 1], o[3 * i + 2]},
-                      V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]}, t);
-  nhit[i] = k;
-  for (int j = 0; j < 4; ++j) ts[4 * i + j] = j < k ? t[j] : 0.0;
-}
-__global__ void test_normal_kernel(long long n, const int32_t* gtype, const double* params, const double* p, double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const V3 r = outward_normal(gtype[i], params + 4 * i, V3{p[3 * i], p[3 * i + 1], p[3 * i + 2]});
-  out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
-}
-__global__ void test_interp_kernel(long long n, const double* x, int m, const double* xs, const double* ys, double inv_dx,
-                                   double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = interp_hinted(x[i], xs, ys, m, inv_dx);
-}
-template <class Rng>
-__global__ void test_rng_kernel(long long n_rays, int n_draws, u64 seed, long long first_index, double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_rays) return;
-  Rng rng;
-  rng.init(seed + (u64)first_index + (u64)i);
-  for (int k = 0; k < n_draws; ++k) out[i * n_draws + k] = rng.next();
-}
-template <class Rng>
-__global__ void test_phase_kernel(long long n, int ptype, double prm, u64 seed, double* out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Rng rng;
-  rng.init(seed + (u64)i);
-  const double g1 = rng.next(), g2 = rng.next();  // uniforms 0 and 1 of the ray's stream
-  const V3 r = phase_direction(ptype, prm, g1, g2);
-  out[3 * i] = r.x; out[3 * i + 1] = r.y; out[3 * i + 2] = r.z;
 }
 
 }  // namespace pvt

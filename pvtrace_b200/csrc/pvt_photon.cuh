@@ -169,7 +169,7 @@ __device__ __forceinline__ Nearest nearest_surface(const SceneView& sv, const V3
 
 // The same reduction for scenes made of axis-aligned boxes only (every LSC scene: world box, slab, coatings), chosen
 // per scene by the kernels' kBoxes instantiation: no primitive switch, no rotation, one reciprocal direction for all.
-__device__ __noinline__ Nearest nearest_surface_boxes_any(const SceneView sv, V3 p, V3 d) {  // rays parallel to a slab: rare
+static __device__ __noinline__ Nearest nearest_surface_boxes_any(const SceneView sv, V3 p, V3 d) {  // rays parallel to a slab: rare
   const int n_nodes = sv.hdr().n_nodes;
   TwoNearest best;
   const V3 inv = slab_reciprocal(d);
@@ -221,7 +221,7 @@ __device__ __forceinline__ double absorption_at(const SceneView& sv, int c, doub
 
 // ---- event log (_kernel.pyx:562-597).  Out of line and by value: only sampled rays ever get here. ----------
 
-__device__ __noinline__ void log_event(const LogColumns& L, long long row, int kind, int hit, int container, int adjacent,
+static __device__ __noinline__ void log_event(const LogColumns& L, long long row, int kind, int hit, int container, int adjacent,
                                        int component, int source, V3 p, V3 d, bool has_normal, V3 normal, double wl,
                                        double travelled, double duration) {
   L.kind[row] = (uint8_t)kind;
@@ -640,30 +640,31 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
 }
 
 // ---- on-device emission of the built-in light delegates (emit.py:22-134; scene.py:141-151) ---------------
-// Uniform k of Philox stream kStreamEmit of ray id: k=0 wavelength, k=1..3 position, k=4,5 direction.
+// Uniform k of Philox stream kStreamEmit of photon `index` of run `run`: k=0 wavelength, k=1..3 position, k=4,5 direction.
 struct EmittedRay {
   V3 pos, dir;
   double wl;
 };
-__device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, u64 id, long long index);
+__device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, const RunSeed& run, long long index);
 
 // out-of-line forms: by reference (refill fallback, register kernel, emit_kernel) and straight into the columns of a
 // shared-memory ring of stride K (so the caller keeps nothing address-taken on its stack)
-__device__ __noinline__ void emit_ray(const SceneView sv, u64 id, long long index, V3& pos, V3& dir, double& wl) {
-  const EmittedRay r = emit_ray_value(sv, id, index);
+static __device__ __noinline__ void emit_ray(const SceneView sv, const RunSeed& run, long long index, V3& pos, V3& dir, double& wl) {
+  const EmittedRay r = emit_ray_value(sv, run, index);
   pos = r.pos; dir = r.dir; wl = r.wl;
 }
-__device__ __noinline__ void emit_ray_to_ring(const SceneView sv, u64 id, long long index, double* dst, int K) {
-  const EmittedRay r = emit_ray_value(sv, id, index);
+static __device__ __noinline__ void emit_ray_to_ring(const SceneView sv, const RunSeed& run, long long index, double* dst, int K) {
+  const EmittedRay r = emit_ray_value(sv, run, index);
   dst[0] = r.pos.x; dst[K] = r.pos.y; dst[2 * K] = r.pos.z;
   dst[3 * K] = r.dir.x; dst[4 * K] = r.dir.y; dst[5 * K] = r.dir.z;
   dst[6 * K] = r.wl;
 }
 
-__device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, u64 id, long long index) {
+__device__ __forceinline__ EmittedRay emit_ray_value(const SceneView& sv, const RunSeed& run, long long index) {
   V3 pos, dir;
   double wl;
   const Header& H = sv.hdr();
+  const u64 id = run.philox_base + (u64)index;
   const int l = (int)(index % H.n_lights);
   const double* q = sv.light(l);
   V3 lp = V3{0.0, 0.0, 0.0}, ld = V3{0.0, 0.0, 1.0};

@@ -15,9 +15,11 @@ LIB_PATH = os.environ.get(
     "PVTRACE_B200_LIB", os.path.join(os.path.dirname(HERE), "csrc", "libpvtrace_b200.so"))
 
 FLAG_REGISTER_KERNEL = 1  # PVT_FLAG_REGISTER_KERNEL: force the one-photon-per-lane kernel
+FLAG_WARP_KERNEL = 2      # PVT_FLAG_WARP_KERNEL: warp_wavefront_kernel (autonomous warps)
+FLAG_CTA_KERNEL = 4       # PVT_FLAG_CTA_KERNEL: wavefront_kernel (two-stage CTA wavefront)
 RNG_PHILOX, RNG_XOSHIRO = 0, 1
 RNG_MODES = {"philox": RNG_PHILOX, "xoshiro": RNG_XOSHIRO}
-NSTATS = 8
+NSTATS = 32
 STAT_STEPS, STAT_RAYS, STAT_LAUNCHES, STAT_EVENTS = 0, 1, 2, 3
 
 _P_I32, _P_F64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
