@@ -284,7 +284,7 @@ def run_b200(args):
         out, _ = e2e_step()
     fence()
     e2e_s = (time.perf_counter() - tic) / e2e_steps
-    h2d = int(np_pos.nbytes + np_dir.nbytes + np_wl.nbytes)
+    h2d = int(out["stats"][_cuda.STAT_H2D_BYTES])  # what crossed PCIe: columns that are constant over the bundle do not
     d2h = int(sum(out[k].nbytes for k in ("rec_distinct", "rec_crossings", "rec_sums", "rec_bins", "stats")))
 
     # ---- reduce timings over ranks (max) ---------------------------------------------------------------------

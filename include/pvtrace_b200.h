@@ -167,11 +167,7 @@ typedef struct pvt_params_t {
 /* Kernel selection.  By default a bundle is traced by the shared-memory wavefront kernel whenever the scene
  * allows it (Philox stream, <= 64 recorders, tables + photon pool fit in shared memory) and by the
  * one-photon-per-lane register kernel otherwise; this flag forces the latter (tests cross-check the two). */
-enum {
-  PVT_FLAG_REGISTER_KERNEL = 1, /* trace_kernel: one photon per lane in registers                                */
-  PVT_FLAG_WARP_KERNEL = 2,     /* warp_wavefront_kernel: autonomous warps, each with its own pool and queues       */
-  PVT_FLAG_CTA_KERNEL = 4       /* wavefront_kernel: two-stage CTA wavefront with service warps                     */
-};
+enum { PVT_FLAG_REGISTER_KERNEL = 1 };
 
 /* Run statistics written by every trace (device counters, not estimates). */
 enum {
@@ -179,6 +175,7 @@ enum {
   PVT_STAT_RAYS = 1,       /* rays retired                                                               */
   PVT_STAT_LAUNCHES = 2,   /* kernels launched by the call                                               */
   PVT_STAT_EVENTS = 3,     /* events generated (logged or not)                                           */
+  PVT_STAT_H2D_BYTES = 4,  /* host entry points: bytes of ray data that crossed PCIe (constant columns do not) */
   PVT_NSTATS = 32
 };
 
@@ -223,6 +220,16 @@ void        pvt_struct_sizes(int32_t sizes[4]);
 int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit,
                      const double* positions, const double* directions, const double* wavelengths,
                      const pvt_params_t* params, pvt_out_t* out, double* elapsed_s);
+
+/* The same bundle over several devices of this process (`n_devices, device_ids`): contiguous index
+ * slices, one host thread per device, per-device cached contexts; tallies are summed and the log rows of every slice
+ * land in place, so `out` is what one device would have produced (integer fields identical, sums to summation order).
+ * `params->device` is ignored.  This is what `engine.simulate(..., workers=k)` maps to (reference: `workers` =
+ * OpenMP threads, pvtrace/engine/api.py:197-246).                                                              */
+int pvt_trace_bundle_devices(const pvt_scene_t* scene, const pvt_emit_t* emit,
+                             const double* positions, const double* directions, const double* wavelengths,
+                             const pvt_params_t* params, int32_t n_devices, const int32_t* device_ids,
+                             pvt_out_t* out, double* elapsed_s);
 
 /* ---------------------------------------------------------------- resident-scene API ------------------ *
  * A context owns the device copy of the tables, the tally accumulators and the event-log buffers on ONE

@@ -7,7 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pvtrace_b200.h"
@@ -58,9 +61,6 @@ struct pvt_context {
   int wave_ctas = 1;        // resident CTAs per SM
   bool wave_boxes = false;  // every node is an axis-aligned box: the kBoxes instantiation (no primitive switch)
   size_t wave_smem = 0;
-  // warp_wavefront_kernel (autonomous warps): shape chosen for the scene, 0 warps: does not fit
-  int wave2_warps = 0, wave2_slots = 0;
-  bool prefer_wave2 = false;
   // event log of the last trace
   long long log_rows = 0, log_rays = 0;
   DeviceBuffer<int32_t> counts, hit, container, adjacent, component, source;
@@ -159,22 +159,6 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
     }
   }
 
-  if (c->R() <= 64) {
-    int want_w = 0, want_n = 0;
-    if (const char* env = getenv("PVT_WAVE2_WARPS")) want_w = atoi(env);
-    if (const char* env = getenv("PVT_WAVE2_SLOTS")) want_n = atoi(env);
-    for (int k = 0; k < wave2_variant_count(); ++k) {
-      const Wave2Variant v = wave2_variant(k);
-      if ((want_w && v.warps != want_w) || (want_n && v.slots != want_n)) continue;
-      const size_t need = wave2_smem(v, c->blob_words, true);
-      if (need + 1024 <= (size_t)prop.sharedMemPerMultiprocessor && need <= (size_t)prop.sharedMemPerBlockOptin) {
-        c->wave2_warps = v.warps; c->wave2_slots = v.slots;
-        break;
-      }
-    }
-  }
-  if (const char* env = getenv("PVT_KERNEL")) c->prefer_wave2 = strcmp(env, "wave2") == 0;
-
   int rc = c->blob.reserve((size_t)c->blob_words);
   c->tally_words = (size_t)10 * c->R() + c->B() + PVT_NSTATS + 1;
   if (!rc) rc = c->tallies.reserve(c->tally_words);
@@ -191,8 +175,6 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
     rc = fail("tally reset failed: %s", cudaGetErrorString(cudaGetLastError()));
   for (int which = 0; which < 4 && !rc; ++which) rc = reg_occupancy(which, c->smem_bytes, &c->blocks_per_sm[which]);
   if (!rc && c->wave_threads > 0) rc = wave_setup(WaveVariant{c->wave_threads, c->wave_pool, c->wave_ctas}, c->wave_smem);
-  if (!rc && c->wave2_warps > 0)
-    rc = wave2_setup(Wave2Variant{c->wave2_warps, c->wave2_slots}, wave2_smem(Wave2Variant{c->wave2_warps, c->wave2_slots}, c->blob_words, true));
   if (!rc && c->smem_bytes > 48 * 1024 &&
       (cudaFuncSetAttribute(intersect_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
        cudaFuncSetAttribute(intersect_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
@@ -212,11 +194,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
 extern "C" int pvt_context_destroy(pvt_context_t* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  c->blob.release(); c->tallies.release(); c->packed.release(); c->slabs.release(); c->arrived.release();
-  c->counts.release(); c->hit.release(); c->container.release(); c->adjacent.release(); c->component.release();
-  c->source.release(); c->kind.release(); c->position.release(); c->direction.release(); c->normal.release();
-  c->wavelength.release(); c->travelled.release(); c->duration.release();
-  delete c;
+  delete c;  // every DeviceBuffer member frees itself
   return 0;
 }
 
@@ -285,33 +263,29 @@ static int wave_grid(const pvt_context* c, const pvt_params_t* P) {
   return (int)(want_blocks < resident ? want_blocks : resident);
 }
 
-// does this bundle go through warp_wavefront_kernel?  (same conditions as the CTA wavefront; chosen by PVT_KERNEL=wave2
-// or the PVT_FLAG_WARP_KERNEL bit)
-static bool use_wave2(const pvt_context* c, const pvt_params_t* P) {
-  if (c->wave2_warps <= 0 || P->rng_mode != PVT_RNG_PHILOX || (P->flags & PVT_FLAG_REGISTER_KERNEL) || P->n <= 0) return false;
-  if (P->n >= (1ll << 32) - 1024) return false;
-  if (P->flags & PVT_FLAG_CTA_KERNEL) return false;
-  return c->prefer_wave2 || (P->flags & PVT_FLAG_WARP_KERNEL) || c->wave_threads <= 0;
-}
-static int wave2_grid(const pvt_context* c, const pvt_params_t* P) {
-  const long long per_cta = (long long)c->wave2_warps * c->wave2_slots;
-  const long long want_blocks = (P->n + per_cta - 1) / per_cta;
-  return (int)(want_blocks < c->sm_count ? want_blocks : c->sm_count);
-}
+// Columns of a host bundle that hold one value for every ray (see "constant columns" below): the value goes to the
+// kernel in TraceArgs instead of the column going over PCIe.
+namespace {
+struct RayConstants {
+  uint32_t mask = 0;  // bit 0: positions, 1: directions, 2: wavelengths
+  double pos[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, wl = 0;
+};
+}  // namespace
 
 static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
-                             const pvt_params_t* P, void* stream, const uint32_t* arrived);
+                             const pvt_params_t* P, void* stream, const uint32_t* arrived, const RayConstants* consts);
 
 extern "C" int pvt_trace_device(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
                                 const pvt_params_t* P, void* stream) {
-  return trace_device_impl(c, d_pos, d_dir, d_wl, P, stream, nullptr);
+  return trace_device_impl(c, d_pos, d_dir, d_wl, P, stream, nullptr, nullptr);
 }
 
 static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double* d_dir, const double* d_wl,
-                             const pvt_params_t* P, void* stream, const uint32_t* arrived) {
+                             const pvt_params_t* P, void* stream, const uint32_t* arrived, const RayConstants* consts) {
   if (!c) return fail("ctx is NULL");
   PVT_TRY(check_params(P));
-  const bool have_rays = d_pos && d_dir && d_wl;
+  const uint32_t cmask = consts ? consts->mask : 0u;
+  const bool have_rays = (d_pos || (cmask & 1u)) && (d_dir || (cmask & 2u)) && (d_wl || (cmask & 4u));
   if (!have_rays && !c->has_emitter) return fail("no ray arrays given and the context has no emitter");
   PVT_CUDA(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -322,7 +296,12 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
   TraceArgs a;
   a.hdr = c->hdr;
   a.blob = c->blob.ptr; a.blob_words = c->blob_words; a.scene_in_smem = c->scene_in_smem;
-  a.pos = have_rays ? d_pos : nullptr; a.dir = have_rays ? d_dir : nullptr; a.wl = have_rays ? d_wl : nullptr;
+  a.pos = have_rays && !(cmask & 1u) ? d_pos : nullptr;
+  a.dir = have_rays && !(cmask & 2u) ? d_dir : nullptr;
+  a.wl = have_rays && !(cmask & 4u) ? d_wl : nullptr;
+  a.const_mask = have_rays ? cmask : 0u;
+  for (int k = 0; k < 3; ++k) { a.cpos[k] = consts ? consts->pos[k] : 0.0; a.cdir[k] = consts ? consts->dir[k] : 0.0; }
+  a.cwl = consts ? consts->wl : 0.0;
   a.n = P->n; a.first_index = P->first_index; a.record_every = P->record_every; a.keys = make_run_seed(P->seed);
   a.sp.maxsteps = P->maxsteps; a.sp.max_events = P->max_events; a.sp.emit_method = P->emit_method;
   a.work_counter = c->d_work();
@@ -336,12 +315,7 @@ static int trace_device_impl(pvt_context_t* c, const double* d_pos, const double
   a.requests = c->requests.ptr;
   int grid = wave_grid(c, P);
   a.arrived = arrived;
-  if (use_wave2(c, P)) {
-    grid = wave2_grid(c, P);
-    const Wave2Variant v{c->wave2_warps, c->wave2_slots};
-    PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
-    PVT_TRY(wave2_launch(v, c->wave_boxes, P->record_every > 0, a, grid, wave2_smem(v, c->blob_words, P->record_every > 0), st));
-  } else if (grid > 0) {
+  if (grid > 0) {
     // persistent CTAs that claim blocks of photons from the work counter (zeroed above) as their pools drain
     PVT_CUDA(cudaMemsetAsync(c->slabs.ptr, 0, (size_t)grid * 10 * c->R() * 8 + 8, st));
     PVT_TRY(wave_launch(WaveVariant{c->wave_threads, c->wave_pool, c->wave_ctas}, c->wave_service, c->wave_boxes,
@@ -510,14 +484,29 @@ struct Timer {
 constexpr int kMaxChunks = 64;           // pieces a host bundle is uploaded + traced in
 constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each (separate launches)
 constexpr size_t kStreamChunkRays = 1 << 16;  // smallest chunk of the streaming upload (one launch, arrival marks)
+constexpr int kMaxDevices = 64;
 
-// The streaming upload needs the copy stream to make progress WHILE the trace kernel runs.  Anything that
-// serialises the two (CUDA_LAUNCH_BLOCKING, a profiler replaying kernels one at a time) would leave the kernel
-// polling until it gives up, so the path is switched off when such a tool is detected, when the user says so
-// (PVT_STREAM_UPLOAD=0), and for good after a bundle that did not complete (which is then re-traced the plain way).
-bool g_stream_upload_ok = true;
-bool stream_upload_allowed() {
-  if (!g_stream_upload_ok) return false;
+// What the host-buffer entry points keep PER DEVICE: the cached context (bundles of the same scene -- engine.simulate_stream,
+// repeated simulate calls -- reuse the uploaded blob and every device buffer), the ray staging buffer, two non-blocking
+// streams and the upload events.  One bundle at a time per device (the mutex); different devices run concurrently, which
+// is how pvt_trace_bundle_devices drives several GPUs from one process.
+struct HostPath {
+  std::mutex mutex;
+  pvt_context* ctx = nullptr;
+  DeviceBuffer<double> rays;  // staging for host rays: [pos 3n | dir 3n | wl n]
+  cudaStream_t s_copy = nullptr, s_run = nullptr;
+  cudaEvent_t uploaded[kMaxChunks] = {};
+  uint32_t* h_marks = nullptr;  // page-locked: the arrival marks must not be staged
+  // The streaming upload needs the copy stream to make progress WHILE the trace kernel runs.  Anything that serialises
+  // the two (CUDA_LAUNCH_BLOCKING, a profiler replaying kernels one at a time) would leave the kernel polling until it
+  // gives up, so the path is switched off when such a tool is detected, when the user says so (PVT_STREAM_UPLOAD=0), and
+  // for good after a bundle that did not complete (which is then re-traced the plain way).
+  bool stream_upload_ok = true;
+};
+HostPath g_paths[kMaxDevices];
+
+bool stream_upload_allowed(const HostPath& path) {
+  if (!path.stream_upload_ok) return false;
   if (const char* env = getenv("PVT_STREAM_UPLOAD")) return atoi(env) != 0;
   if (const char* env = getenv("CUDA_LAUNCH_BLOCKING")) { if (atoi(env) != 0) return false; }
   if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NVTX_INJECTION64_PATH"))
@@ -525,62 +514,161 @@ bool stream_upload_allowed() {
   return true;
 }
 
-// One cached context per process: bundles of the same scene (engine.simulate_stream, repeated simulate calls)
-// reuse the uploaded blob and every device buffer.
-std::mutex g_cache_mutex;
-pvt_context* g_cached = nullptr;
-DeviceBuffer<double> g_rays;  // staging for host rays: [pos 3n | dir 3n | wl n]
-int g_rays_device = -1;
+int acquire_path(int device, HostPath** out) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail("no CUDA device is usable (pvtrace_b200 has no CPU fallback)");
+  if (device < 0 || device >= n_dev || device >= kMaxDevices) return fail("device %d out of range (have %d)", device, n_dev);
+  *out = &g_paths[device];
+  return 0;
+}
 
-int acquire_context(const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context** out) {
+// (call with path.mutex held)
+int acquire_context(HostPath& path, const pvt_scene_t* scene, const pvt_emit_t* emit, int device, pvt_context** out) {
   PVT_TRY(validate_scene(scene));
   std::vector<double> blob = pack_scene(*scene, emit);
-  if (g_cached && g_cached->device == device && g_cached->host_blob.size() == blob.size() &&
-      memcmp(g_cached->host_blob.data(), blob.data(), blob.size() * 8) == 0 && g_cached->has_emitter == (emit != nullptr)) {
-    *out = g_cached;
+  pvt_context*& cached = path.ctx;
+  if (cached && cached->host_blob.size() == blob.size() &&
+      memcmp(cached->host_blob.data(), blob.data(), blob.size() * 8) == 0 && cached->has_emitter == (emit != nullptr)) {
+    *out = cached;
     return 0;
   }
-  if (g_cached) { pvt_context_destroy(g_cached); g_cached = nullptr; }
-  PVT_TRY(pvt_context_create(scene, emit, device, &g_cached));
-  *out = g_cached;
+  if (cached) { pvt_context_destroy(cached); cached = nullptr; }
+  PVT_TRY(pvt_context_create(scene, emit, device, &cached));
+  *out = cached;
   return 0;
+}
+
+int ensure_streams(HostPath& path) {
+  if (path.s_copy) return 0;
+  PVT_CUDA(cudaStreamCreateWithFlags(&path.s_copy, cudaStreamNonBlocking));
+  PVT_CUDA(cudaStreamCreateWithFlags(&path.s_run, cudaStreamNonBlocking));
+  for (auto& e : path.uploaded) PVT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  PVT_CUDA(cudaHostAlloc((void**)&path.h_marks, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
+  return 0;
+}
+
+// ---- constant columns --------------------------------------------------------------------------------------
+// A bundle from a point source carries the same position in every row, a monochromatic one the same wavelength, a
+// collimated one the same direction: 24 + 8 (+ 24) of the 56 bytes per ray that cross PCIe say nothing.  The host
+// finds such columns and passes ONE value to the kernel instead (TraceArgs::const_mask).  Finding them means reading
+// every row, and at host-memory speed that is as long as the upload it saves -- so it is done OPTIMISTICALLY: a column
+// whose first rows agree is taken as constant, the trace starts at once on the remaining columns, and worker threads
+// check the rest of the column while the device is busy.  In the (contrived) case that a later row differs, the result
+// is discarded and the bundle traced again with every column uploaded.
+constexpr size_t kProbeRows = 4096;       // rows compared up front
+constexpr size_t kElideMinRays = 1 << 18;  // smaller bundles are not worth the threads
+constexpr size_t kScanBlockRows = 1 << 14;
+
+class ConstantScan {
+ public:
+  RayConstants found;
+  // decides the candidates from the first rows and starts checking the rest on `threads - 1` workers
+  void start(const double* pos, const double* dir, const double* wl, size_t n, int threads) {
+    cols_[0] = Column{pos, 3}; cols_[1] = Column{dir, 3}; cols_[2] = Column{wl, 1};
+    n_ = n;
+    const size_t probe = n < kProbeRows ? n : kProbeRows;
+    for (int k = 0; k < 3; ++k) {
+      fill_template(k);
+      if (rows_equal(k, 0, probe)) found.mask |= 1u << k;
+    }
+    for (int k = 0; k < 3; ++k) { found.pos[k] = pos[k]; found.dir[k] = dir[k]; }
+    found.wl = wl[0];
+    blocks_per_col_ = (n + kScanBlockRows - 1) / kScanBlockRows;
+    next_.store(0);
+    failed_.store(false);
+    if (!found.mask) return;
+    for (int t = 1; t < threads; ++t) workers_.emplace_back([this] { work(); });
+  }
+  // the calling thread helps, then joins the workers; false: some candidate column was not constant after all
+  bool finish() {
+    if (found.mask) work();
+    for (auto& w : workers_) w.join();
+    workers_.clear();
+    return !failed_.load();
+  }
+  ~ConstantScan() { for (auto& w : workers_) if (w.joinable()) w.join(); }
+
+ private:
+  struct Column { const double* data; int width; };
+  static constexpr size_t kTemplateRows = 512;
+  Column cols_[3];
+  double tmpl_[3][kTemplateRows * 3];
+  size_t n_ = 0, blocks_per_col_ = 0;
+  std::atomic<size_t> next_{0};
+  std::atomic<bool> failed_{false};
+  std::vector<std::thread> workers_;
+
+  void fill_template(int k) {
+    const int w = cols_[k].width;
+    for (size_t r = 0; r < kTemplateRows; ++r)
+      for (int j = 0; j < w; ++j) tmpl_[k][r * w + j] = cols_[k].data[j];
+  }
+  // bitwise comparison (memcmp is vectorised): -0.0 differs from 0.0 and a NaN equals itself, which is what is wanted
+  bool rows_equal(int k, size_t lo, size_t hi) const {
+    const int w = cols_[k].width;
+    for (size_t r = lo; r < hi; r += kTemplateRows) {
+      const size_t m = hi - r < kTemplateRows ? hi - r : kTemplateRows;
+      if (memcmp(cols_[k].data + r * w, tmpl_[k], m * w * sizeof(double)) != 0) return false;
+    }
+    return true;
+  }
+  void work() {
+    for (;;) {
+      if (failed_.load(std::memory_order_relaxed)) return;
+      const size_t b = next_.fetch_add(1);
+      if (b >= 3 * blocks_per_col_) return;
+      const int k = (int)(b / blocks_per_col_);
+      if (!(found.mask & (1u << k))) continue;
+      const size_t lo = (b % blocks_per_col_) * kScanBlockRows, hi = lo + kScanBlockRows < n_ ? lo + kScanBlockRows : n_;
+      if (!rows_equal(k, lo, hi)) { failed_.store(true); return; }
+    }
+  }
+};
+
+int scan_threads() {
+  if (const char* env = getenv("PVT_SCAN_THREADS")) { const int v = atoi(env); if (v >= 1 && v <= 64) return v; }
+  const unsigned hw = std::thread::hardware_concurrency();
+  const unsigned want = hw / 2 < 8 ? hw / 2 : 8;
+  return want < 1 ? 1 : (int)want;
+}
+bool elision_allowed() {
+  if (const char* env = getenv("PVT_ELIDE_CONSTANT")) return atoi(env) != 0;
+  return true;
 }
 }  // namespace
 
-extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, const double* positions,
-                                const double* directions, const double* wavelengths, const pvt_params_t* params,
-                                pvt_out_t* out, double* elapsed_s) {
+// One bundle on one device, host buffers in and out.  h2d_bytes: what actually crossed PCIe for the rays.
+static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, const double* positions,
+                             const double* directions, const double* wavelengths, const pvt_params_t* params,
+                             pvt_out_t* out, double* elapsed_s) {
   PVT_TRY(check_params(params));
   if (!out) return fail("out is NULL");
   const bool have_rays = positions && directions && wavelengths;
   if (!have_rays && !emit) return fail("either ray arrays or an emitter are required");
-  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  HostPath* path_ptr = nullptr;
+  PVT_TRY(acquire_path(params->device, &path_ptr));
+  HostPath& path = *path_ptr;
+  std::lock_guard<std::mutex> lock(path.mutex);
+  PVT_CUDA(cudaSetDevice(params->device));
   pvt_context* c = nullptr;
-  PVT_TRY(acquire_context(scene, emit, params->device, &c));
-  PVT_CUDA(cudaSetDevice(c->device));
-  // two non-blocking streams: host rays are uploaded in chunks on one while the previous chunk is traced on the
-  // other (overlap needs page-locked host memory; with pageable memory the copies simply serialise)
-  static cudaStream_t s_copy = nullptr, s_run = nullptr;
-  static cudaEvent_t s_uploaded[kMaxChunks] = {nullptr};
-  static int s_device = -1;
-  if (s_device != c->device) {
-    if (s_copy) { cudaStreamDestroy(s_copy); cudaStreamDestroy(s_run); for (auto& e : s_uploaded) cudaEventDestroy(e); }
-    PVT_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    PVT_CUDA(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
-    for (auto& e : s_uploaded) PVT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    s_device = c->device;
-  }
+  PVT_TRY(acquire_context(path, scene, emit, params->device, &c));
+  // two non-blocking streams: host rays are uploaded in chunks on one while the trace runs on the other (overlap needs
+  // page-locked host memory; with pageable memory the copies simply serialise)
+  PVT_TRY(ensure_streams(path));
+  cudaStream_t s_copy = path.s_copy, s_run = path.s_run;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
   PVT_CUDA(cudaEventCreate(&t0));
   PVT_CUDA(cudaEventCreate(&t1));
   PVT_CUDA(cudaEventRecord(t0, s_run));
   int rc = pvt_context_reset(c, s_run);
   const size_t n = (size_t)params->n;
+  long long h2d_bytes = 0;
   // Opt-in (PVT_ZERO_COPY=1): page-locked host arrays (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are
   // read by the kernel IN PLACE, the warps that fill the shared-memory ray ring pulling them over PCIe a whole ring
   // ahead of their use.  Measured 42-45 GB/s against the copy engine's 55 GB/s, so the streaming upload below
   // is the default.
   bool streamed = false;
+  ConstantScan scan;
   const double *z_pos = nullptr, *z_dir = nullptr, *z_wl = nullptr;
   if (!rc && have_rays && n > 0 && getenv("PVT_ZERO_COPY") && atoi(getenv("PVT_ZERO_COPY")) == 1) {
     const void* host[3] = {positions, directions, wavelengths};
@@ -596,59 +684,60 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   }
   if (!rc && z_pos) {
     rc = pvt_trace_device(c, z_pos, z_dir, z_wl, params, s_run);
-  } else if (!rc && have_rays && n > 0 && (wave_grid(c, params) > 0 || use_wave2(c, params)) && stream_upload_allowed()) {
+    h2d_bytes = 56ll * (long long)n;
+  } else if (!rc && have_rays && n > 0 && wave_grid(c, params) > 0 && stream_upload_allowed(path)) {
     // Streaming upload: the trace kernel starts at once and polls an arrival mark; the copy engine delivers the
-    // arrays front to back in chunks (three plain copies each) followed, in stream order, by the new mark = rays
-    // complete so far.  CTAs claim photons in index order, so they consume the prefix as it lands.  Upload and trace
-    // overlap completely: total time ~ max(PCIe, kernel) + the trace of the LAST chunk -- hence chunks that start
-    // small (the kernel gets going at once), double up to a fifth of what is left (few, efficient copies) and
-    // shrink again towards the end (little left to trace when the last byte lands).
+    // arrays front to back in chunks (plain copies of the columns that are not constant) followed, in stream order, by
+    // the new mark = rays complete so far.  CTAs claim photons in index order, so they consume the prefix as it lands.
+    // Upload and trace overlap completely: total time ~ max(PCIe, kernel) + the trace of the LAST chunk -- hence chunks
+    // that start small (the kernel gets going at once), double up to a fifth of what is left (few, efficient copies)
+    // and shrink again towards the end (little left to trace when the last byte lands).
     streamed = true;
-    static uint32_t* h_marks = nullptr;  // page-locked: the mark copies must not be staged
-    if (!h_marks) PVT_CUDA(cudaHostAlloc((void**)&h_marks, kMaxChunks * sizeof(uint32_t), cudaHostAllocDefault));
-    if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
-    rc = g_rays.reserve(7 * n);
-    double *d_pos = g_rays.ptr, *d_dir = g_rays.ptr + 3 * n, *d_wl = g_rays.ptr + 6 * n;
+    if (n >= kElideMinRays && elision_allowed()) scan.start(positions, directions, wavelengths, n, scan_threads());
+    const RayConstants& consts = scan.found;
+    rc = path.rays.reserve(7 * n);
+    double *d_pos = path.rays.ptr, *d_dir = path.rays.ptr + 3 * n, *d_wl = path.rays.ptr + 6 * n;
     size_t min_chunk = kStreamChunkRays, shrink_div = 5;
     if (const char* env = getenv("PVT_UPLOAD_MIN_CHUNK")) { const long v = atol(env); if (v >= 1024) min_chunk = (size_t)v; }
     if (const char* env = getenv("PVT_UPLOAD_SHRINK")) { const int v = atoi(env); if (v >= 2 && v <= 64) shrink_div = (size_t)v; }
     int chunks = 0;
     cudaError_t e = cudaSuccess;
-    static cudaEvent_t dbg[2] = {nullptr, nullptr};  // PVT_DEBUG_TIMING=1: how long the copy stream took
-    const bool dbg_on = getenv("PVT_DEBUG_TIMING") != nullptr;
-    if (dbg_on && !dbg[0]) { cudaEventCreate(&dbg[0]); cudaEventCreate(&dbg[1]); }
-    if (dbg_on) cudaEventRecord(dbg[0], s_copy);
+    uint32_t* h_marks = path.h_marks;
     if (!rc) e = cudaMemsetAsync(c->arrived.ptr, 0, 4, s_copy);
-    if (!rc && e == cudaSuccess) e = cudaEventRecord(s_uploaded[0], s_copy);
-    if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(s_run, s_uploaded[0], 0);
-    if (!rc && e == cudaSuccess) rc = trace_device_impl(c, d_pos, d_dir, d_wl, params, s_run, c->arrived.ptr);
-    size_t lo = 0, grow = min_chunk;
-    while (lo < n && !rc && e == cudaSuccess) {
-      const size_t left = n - lo;
-      size_t m = left / shrink_div > min_chunk ? left / shrink_div : min_chunk;
-      if (m > grow) m = grow;
-      grow *= 2;
-      if (m > left || chunks == kMaxChunks - 1 || left - m < min_chunk / 2) m = left;
-      e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir + 3 * lo, directions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
-      if (e == cudaSuccess) e = cudaMemcpyAsync(d_wl + lo, wavelengths + lo, 8 * m, cudaMemcpyHostToDevice, s_copy);
-      lo += m;
-      h_marks[chunks] = (uint32_t)lo;
-      if (e == cudaSuccess) e = cudaMemcpyAsync(c->arrived.ptr, h_marks + chunks, 4, cudaMemcpyHostToDevice, s_copy);
-      ++chunks;
+    if (!rc && e == cudaSuccess) e = cudaEventRecord(path.uploaded[0], s_copy);
+    if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(s_run, path.uploaded[0], 0);
+    if (!rc && e == cudaSuccess) rc = trace_device_impl(c, d_pos, d_dir, d_wl, params, s_run, c->arrived.ptr, &consts);
+    if (consts.mask == 7u) {  // nothing to upload at all: every ray "has arrived"
+      h_marks[0] = (uint32_t)n;
+      if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(c->arrived.ptr, h_marks, 4, cudaMemcpyHostToDevice, s_copy);
+    } else {
+      size_t lo = 0, grow = min_chunk;
+      while (lo < n && !rc && e == cudaSuccess) {
+        const size_t left = n - lo;
+        size_t m = left / shrink_div > min_chunk ? left / shrink_div : min_chunk;
+        if (m > grow) m = grow;
+        grow *= 2;
+        if (m > left || chunks == kMaxChunks - 1 || left - m < min_chunk / 2) m = left;
+        if (!(consts.mask & 1u)) {
+          e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
+          h2d_bytes += 24ll * (long long)m;
+        }
+        if (e == cudaSuccess && !(consts.mask & 2u)) {
+          e = cudaMemcpyAsync(d_dir + 3 * lo, directions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
+          h2d_bytes += 24ll * (long long)m;
+        }
+        if (e == cudaSuccess && !(consts.mask & 4u)) {
+          e = cudaMemcpyAsync(d_wl + lo, wavelengths + lo, 8 * m, cudaMemcpyHostToDevice, s_copy);
+          h2d_bytes += 8ll * (long long)m;
+        }
+        lo += m;
+        h_marks[chunks] = (uint32_t)lo;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->arrived.ptr, h_marks + chunks, 4, cudaMemcpyHostToDevice, s_copy);
+        ++chunks;
+      }
     }
-    if (dbg_on) {
-      cudaEventRecord(dbg[1], s_copy);
-      cudaEventSynchronize(dbg[1]);
-      cudaStreamSynchronize(s_run);
-      float up = 0.f, t_start = 0.f;
-      cudaEventElapsedTime(&up, dbg[0], dbg[1]);
-      cudaEventElapsedTime(&t_start, t0, dbg[0]);
-      cudaEventRecord(t1, s_run); cudaEventSynchronize(t1);
-      float total = 0.f;
-      cudaEventElapsedTime(&total, t0, t1);
-      fprintf(stderr, "[pvt] upload started %.3f ms after t0, took %.3f ms (%d chunks); trace done at %.3f ms\n", t_start, up, chunks, total);
-    }
+    if (getenv("PVT_DEBUG_TIMING")) fprintf(stderr, "[pvt] device %d: constant columns mask %u, %d upload chunks, %lld bytes\n",
+                                            params->device, consts.mask, chunks, h2d_bytes);
     if (!rc && e != cudaSuccess) {
       // never leave the kernel polling: publish "everything arrived" so it drains, then report
       h_marks[kMaxChunks - 1] = 0xffffffffu;
@@ -656,9 +745,8 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
       rc = fail("ray upload failed: %s", cudaGetErrorString(e));
     }
   } else if (!rc && have_rays && n > 0) {
-    if (g_rays_device != c->device) { g_rays.release(); g_rays_device = c->device; }
-    rc = g_rays.reserve(7 * n);
-    double *d_pos = g_rays.ptr, *d_dir = g_rays.ptr + 3 * n, *d_wl = g_rays.ptr + 6 * n;
+    rc = path.rays.reserve(7 * n);
+    double *d_pos = path.rays.ptr, *d_dir = path.rays.ptr + 3 * n, *d_wl = path.rays.ptr + 6 * n;
     // the event log is indexed by the ray's position in the bundle, so logged bundles go in one piece
     int chunks = (params->record_every == 0 && n >= (size_t)kMinChunkRays * 2) ? (int)(n / kMinChunkRays) : 1;
     if (chunks > kMaxChunks) chunks = kMaxChunks;
@@ -671,9 +759,10 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
       cudaError_t e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_dir + 3 * lo, directions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
       if (e == cudaSuccess) e = cudaMemcpyAsync(d_wl + lo, wavelengths + lo, 8 * m, cudaMemcpyHostToDevice, s_copy);
-      if (e == cudaSuccess) e = cudaEventRecord(s_uploaded[k], s_copy);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, s_uploaded[k], 0);
+      if (e == cudaSuccess) e = cudaEventRecord(path.uploaded[k], s_copy);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(s_run, path.uploaded[k], 0);
       if (e != cudaSuccess) { rc = fail("ray upload failed: %s", cudaGetErrorString(e)); break; }
+      h2d_bytes += 56ll * (long long)m;
       pvt_params_t part = *params;
       part.n = (int64_t)m;
       part.first_index = params->first_index + (int64_t)lo;
@@ -682,22 +771,32 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   } else if (!rc) {
     rc = pvt_trace_device(c, nullptr, nullptr, nullptr, params, s_run);
   }
+  // (the calling thread joins the check of the constant columns while the device works)
+  const bool columns_ok = scan.finish();
   if (!rc) rc = pvt_context_read(c, out, s_run);
   if (!rc && n > 0) {  // every ray must have been traced
     u64 traced = 0;
     if (cudaMemcpy(&traced, c->d_stats() + PVT_STAT_RAYS, 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
       rc = fail("reading the ray counter failed: %s", cudaGetErrorString(cudaGetLastError()));
-    } else if (traced != (u64)n && streamed) {
-      // the kernel gave up polling for rays: something serialised upload and trace.  Trace again the plain way.
-      g_stream_upload_ok = false;
+    } else if (streamed && (traced != (u64)n || !columns_ok)) {
+      // Either the kernel gave up polling for rays (something serialised upload and trace: never stream again), or a
+      // column taken as constant was not.  Trace again the plain way, every column uploaded.
+      if (traced != (u64)n) path.stream_upload_ok = false;
       cudaStreamSynchronize(s_copy);
-      rc = pvt_context_reset(c, s_run);
-      if (!rc) rc = pvt_trace_device(c, g_rays.ptr, g_rays.ptr + 3 * n, g_rays.ptr + 6 * n, params, s_run);
+      double* r = path.rays.ptr;
+      cudaError_t e = cudaMemcpyAsync(r, positions, 24 * n, cudaMemcpyHostToDevice, s_run);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(r + 3 * n, directions, 24 * n, cudaMemcpyHostToDevice, s_run);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(r + 6 * n, wavelengths, 8 * n, cudaMemcpyHostToDevice, s_run);
+      if (e != cudaSuccess) rc = fail("ray upload failed: %s", cudaGetErrorString(e));
+      h2d_bytes += 56ll * (long long)n;
+      if (!rc) rc = pvt_context_reset(c, s_run);
+      if (!rc) rc = pvt_trace_device(c, r, r + 3 * n, r + 6 * n, params, s_run);
       if (!rc) rc = pvt_context_read(c, out, s_run);
     } else if (traced != (u64)n) {
       rc = fail("traced %llu of %zu rays", traced, n);
     }
   }
+  if (!rc && out->stats) out->stats[PVT_STAT_H2D_BYTES] = h2d_bytes;
   if (!rc) {
     cudaError_t e = cudaEventRecord(t1, s_run);
     if (e == cudaSuccess) e = cudaEventSynchronize(t1);
@@ -712,6 +811,101 @@ extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
   return rc;
+}
+
+extern "C" int pvt_trace_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, const double* positions,
+                                const double* directions, const double* wavelengths, const pvt_params_t* params,
+                                pvt_out_t* out, double* elapsed_s) {
+  return trace_host_bundle(scene, emit, positions, directions, wavelengths, params, out, elapsed_s);
+}
+
+// Several devices, one process: contiguous index slices of the bundle, one host thread per device (each with its own
+// cached context, streams and staging), tallies summed on the host -- they have to come to the host anyway, 62 KB per
+// device for the LSC configs -- and every device writing the log rows of its own slice straight into the caller's arrays.
+extern "C" int pvt_trace_bundle_devices(const pvt_scene_t* scene, const pvt_emit_t* emit, const double* positions,
+                                        const double* directions, const double* wavelengths, const pvt_params_t* params,
+                                        int32_t n_devices, const int32_t* device_ids, pvt_out_t* out, double* elapsed_s) {
+  PVT_TRY(check_params(params));
+  if (!out) return fail("out is NULL");
+  if (n_devices <= 0 || !device_ids) return fail("n_devices must be >= 1 and device_ids non-NULL");
+  if (n_devices > kMaxDevices) return fail("at most %d devices", kMaxDevices);
+  for (int a = 0; a < n_devices; ++a)
+    for (int b = a + 1; b < n_devices; ++b)
+      if (device_ids[a] == device_ids[b]) return fail("device %d listed twice", device_ids[a]);
+  if (n_devices == 1 || params->n == 0) {
+    pvt_params_t one = *params;
+    one.device = device_ids[0];
+    return trace_host_bundle(scene, emit, positions, directions, wavelengths, &one, out, elapsed_s);
+  }
+  PVT_TRY(validate_scene(scene));
+  const bool have_rays = positions && directions && wavelengths;
+  const int R = scene->n_recorders, B = scene->total_bins;
+  const long long n = params->n, every = params->record_every;
+  // slice boundaries: equal shares, rounded to the logging stride so that every slice samples the same rays as the
+  // whole bundle would (ray i is logged iff i % record_every == 0)
+  std::vector<long long> cut(n_devices + 1);
+  for (int d = 0; d <= n_devices; ++d) {
+    long long at = n * d / n_devices;
+    if (every > 1 && d < n_devices) at = (at + every - 1) / every * every;
+    cut[d] = at < n ? at : n;
+  }
+  cut[n_devices] = n;
+  struct Part {
+    std::vector<int64_t> distinct, cross, bins, stats;
+    std::vector<double> sums;
+    int32_t no_counts = 0;
+    double elapsed = 0.0;
+    int rc = 0;
+    std::string error;
+  };
+  std::vector<Part> parts(n_devices);
+  std::vector<std::thread> threads;
+  for (int d = 0; d < n_devices; ++d) {
+    Part& part = parts[d];
+    part.distinct.assign(R > 0 ? R : 1, 0); part.cross.assign(R > 0 ? R : 1, 0); part.sums.assign(R > 0 ? 8 * R : 1, 0.0);
+    part.bins.assign(B > 0 ? B : 1, 0); part.stats.assign(PVT_NSTATS, 0);
+    threads.emplace_back([&, d] {
+      Part& mine = parts[d];
+      const long long lo = cut[d], m = cut[d + 1] - cut[d];
+      if (m <= 0) return;
+      pvt_params_t p = *params;
+      p.n = m; p.first_index = params->first_index + lo; p.device = device_ids[d];
+      pvt_out_t o = *out;
+      o.rec_distinct = mine.distinct.data(); o.rec_crossings = mine.cross.data(); o.rec_sums = mine.sums.data();
+      o.rec_bins = mine.bins.data(); o.stats = mine.stats.data();
+      if (every > 0 && out->kind) {  // the slice's log rows, in place
+        const long long ray0 = lo / every, row0 = ray0 * params->max_events;
+        o.counts = out->counts + ray0; o.kind = out->kind + row0;
+        o.hit = out->hit + row0; o.container = out->container + row0; o.adjacent = out->adjacent + row0;
+        o.component = out->component + row0; o.source = out->source + row0;
+        o.position = out->position + 3 * row0; o.direction = out->direction + 3 * row0; o.normal = out->normal + 3 * row0;
+        o.wavelength = out->wavelength + row0; o.travelled = out->travelled + row0; o.duration = out->duration + row0;
+      } else {
+        o.counts = &mine.no_counts;
+      }
+      mine.rc = trace_host_bundle(scene, emit, have_rays ? positions + 3 * lo : nullptr, have_rays ? directions + 3 * lo : nullptr,
+                                  have_rays ? wavelengths + lo : nullptr, &p, &o, &mine.elapsed);
+      if (mine.rc) mine.error = pvt_last_error();  // (the message is thread-local)
+    });
+  }
+  for (auto& t : threads) t.join();
+  for (int d = 0; d < n_devices; ++d)
+    if (parts[d].rc) return fail("device %d: %s", device_ids[d], parts[d].error.c_str());
+  for (int r = 0; r < R; ++r) { out->rec_distinct[r] = 0; out->rec_crossings[r] = 0; }
+  for (int k = 0; k < 8 * R; ++k) out->rec_sums[k] = 0.0;
+  for (int b = 0; b < B; ++b) out->rec_bins[b] = 0;
+  if (out->stats) for (int k = 0; k < PVT_NSTATS; ++k) out->stats[k] = 0;
+  double slowest = 0.0;
+  for (int d = 0; d < n_devices; ++d) {
+    const Part& part = parts[d];
+    for (int r = 0; r < R; ++r) { out->rec_distinct[r] += part.distinct[r]; out->rec_crossings[r] += part.cross[r]; }
+    for (int k = 0; k < 8 * R; ++k) out->rec_sums[k] += part.sums[k];
+    for (int b = 0; b < B; ++b) out->rec_bins[b] += part.bins[b];
+    if (out->stats) for (int k = 0; k < PVT_NSTATS; ++k) out->stats[k] += part.stats[k];
+    slowest = part.elapsed > slowest ? part.elapsed : slowest;
+  }
+  if (elapsed_s) *elapsed_s = slowest;
+  return 0;
 }
 
 extern "C" int pvt_emit_bundle(const pvt_emit_t* emit, double* positions, double* directions, double* wavelengths, int64_t n,
@@ -750,9 +944,12 @@ extern "C" int pvt_intersect_bundle(const pvt_scene_t* scene, const double* posi
                                     double* t0, int32_t* hit, int32_t* container, int32_t* adjacent, int device,
                                     double* elapsed_s) {
   if (n < 0) return fail("n must be >= 0");
-  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  HostPath* path = nullptr;
+  PVT_TRY(acquire_path(device, &path));
+  std::lock_guard<std::mutex> lock(path->mutex);
+  PVT_CUDA(cudaSetDevice(device));
   pvt_context* c = nullptr;
-  PVT_TRY(acquire_context(scene, nullptr, device, &c));
+  PVT_TRY(acquire_context(*path, scene, nullptr, device, &c));
   PVT_CUDA(cudaSetDevice(c->device));
   if (n == 0) return 0;
   DeviceBuffer<double> in, d_t0;

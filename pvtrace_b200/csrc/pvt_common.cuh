@@ -27,6 +27,10 @@ template <class T>
 struct DeviceBuffer {
   T* ptr = nullptr;
   size_t count = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }  // (owners set their device current first; at process exit the runtime may be gone: harmless)
   int reserve(size_t n) {
     if (n <= count && ptr) return 0;
     if (ptr) cudaFree(ptr);

@@ -45,9 +45,14 @@ struct TraceArgs {
   // many leading rays are complete into *arrived.  CTAs claim blocks of photons in index order from `work_counter`
   // and never touch a ray at or beyond the mark.  arrived == nullptr: all rays are there.
   const uint32_t* arrived;
-  const double* pos;   // [n,3] or null (=> emit on device)
+  const double* pos;   // [n,3]; all three null => rays are sampled on the device
   const double* dir;
   const double* wl;
+  // Columns of the caller's arrays that hold ONE value for every ray (a point source, a monochromatic light) never
+  // cross PCIe: the host passes the value instead (bit 0: positions, 1: directions, 2: wavelengths; the matching
+  // pointer is then unused).  pvt_trace_bundle finds them (pvt_api.cu, "constant columns").
+  uint32_t const_mask;
+  double cpos[3], cdir[3], cwl;
   long long n, first_index, record_every;
   RunSeed keys;  // the run's seed and its window of the Philox counter space
   StepParams sp;
@@ -60,6 +65,7 @@ struct TraceArgs {
   u64* g_bins;      // [total_bins]
   u64* g_stats;     // [PVT_NSTATS]
   LogColumns log;
+  __host__ __device__ __forceinline__ bool has_rays() const { return pos || dir || wl || const_mask == 7u; }
 };
 
 // ---- shared-memory staging of the scene blob through the TMA engine ---------------------------------------
@@ -276,10 +282,12 @@ __device__ __forceinline__ void push_queues(const uint16_t* qv_, const uint16_t*
 // initial state of photon i of the bundle (global arrays or the emitter); out of line: the common path takes
 // fresh rays from the shared-memory ring that the spare warps keep filled
 static __device__ __noinline__ void fetch_ray(const TraceArgs& a, const SceneView sv, long long i, V3& p, V3& d, double& wl) {
-  if (a.pos) {
-    p = V3{__ldcg(a.pos + 3 * i), __ldcg(a.pos + 3 * i + 1), __ldcg(a.pos + 3 * i + 2)};
-    d = V3{__ldcg(a.dir + 3 * i), __ldcg(a.dir + 3 * i + 1), __ldcg(a.dir + 3 * i + 2)};
-    wl = __ldcg(a.wl + i);
+  if (a.has_rays()) {
+    p = (a.const_mask & 1u) ? V3{a.cpos[0], a.cpos[1], a.cpos[2]}
+                            : V3{__ldcg(a.pos + 3 * i), __ldcg(a.pos + 3 * i + 1), __ldcg(a.pos + 3 * i + 2)};
+    d = (a.const_mask & 2u) ? V3{a.cdir[0], a.cdir[1], a.cdir[2]}
+                            : V3{__ldcg(a.dir + 3 * i), __ldcg(a.dir + 3 * i + 1), __ldcg(a.dir + 3 * i + 2)};
+    wl = (a.const_mask & 4u) ? a.cwl : __ldcg(a.wl + i);
   } else {
     emit_ray(sv, a.keys, a.first_index + i, p, d, wl);
   }
@@ -382,12 +390,14 @@ template <int K, bool kInlineEmitter = false>
 __device__ __forceinline__ void produce_ray(const TraceArgs& a, const SceneView& sv, const PoolView& pool, uint32_t o) {
   const long long i = sequence_photon(pool.counters, o);
   double* r = pool.ring + (o & (K - 1));
-  if (a.pos) {
+  if (a.has_rays()) {
     // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles);
     // L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived
-    r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2);
-    r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2);
-    r[6 * K] = __ldcg(a.wl + i);
+    if (a.const_mask & 1u) { r[0] = a.cpos[0]; r[K] = a.cpos[1]; r[2 * K] = a.cpos[2]; }
+    else { r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2); }
+    if (a.const_mask & 2u) { r[3 * K] = a.cdir[0]; r[4 * K] = a.cdir[1]; r[5 * K] = a.cdir[2]; }
+    else { r[3 * K] = __ldcg(a.dir + 3 * i); r[4 * K] = __ldcg(a.dir + 3 * i + 1); r[5 * K] = __ldcg(a.dir + 3 * i + 2); }
+    r[6 * K] = (a.const_mask & 4u) ? a.cwl : __ldcg(a.wl + i);
   } else if (kInlineEmitter) {
     const EmittedRay e = emit_ray_value(sv, a.keys, a.first_index + i);
     r[0] = e.pos.x; r[K] = e.pos.y; r[2 * K] = e.pos.z;
@@ -834,10 +844,10 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const __grid_const
       }
       if (mine) {
         if (idx >= 0) {
-          if (a.pos) {
-            ph.p = V3{a.pos[3 * idx], a.pos[3 * idx + 1], a.pos[3 * idx + 2]};
-            ph.d = V3{a.dir[3 * idx], a.dir[3 * idx + 1], a.dir[3 * idx + 2]};
-            ph.wl = a.wl[idx];
+          if (a.has_rays()) {
+            ph.p = (a.const_mask & 1u) ? V3{a.cpos[0], a.cpos[1], a.cpos[2]} : V3{a.pos[3 * idx], a.pos[3 * idx + 1], a.pos[3 * idx + 2]};
+            ph.d = (a.const_mask & 2u) ? V3{a.cdir[0], a.cdir[1], a.cdir[2]} : V3{a.dir[3 * idx], a.dir[3 * idx + 1], a.dir[3 * idx + 2]};
+            ph.wl = (a.const_mask & 4u) ? a.cwl : a.wl[idx];
           } else {
             emit_ray(sv, a.keys, a.first_index + idx, ph.p, ph.d, ph.wl);
           }

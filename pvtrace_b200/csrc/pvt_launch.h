@@ -1,5 +1,5 @@
 // pvt_launch.h -- host-side launch entry points of the tracer kernels.  Each family of template instantiations lives in
-// its own translation unit (pvt_wave.cu, pvt_wave2.cu, pvt_reg.cu) so that they compile in parallel; pvt_api.cu calls
+// its own translation unit (pvt_wave.cu, pvt_reg.cu) so that they compile in parallel; pvt_api.cu calls
 // them through these functions.
 #pragma once
 #include <cuda_runtime.h>
@@ -19,14 +19,6 @@ int wave_setup(const WaveVariant& v, size_t smem);
 int wave_service_threads();
 int wave_launch(const WaveVariant& v, int service, bool boxes, bool log, const TraceArgs& a, int grid, size_t smem,
                 cudaStream_t st);
-
-// warp_wavefront_kernel<W, N, kLog, kBoxes>: (warps per CTA, photon slots per warp), preferred first
-struct Wave2Variant { int warps, slots; };
-int wave2_variant_count();
-Wave2Variant wave2_variant(int k);
-size_t wave2_smem(const Wave2Variant& v, int blob_words, bool log);  // dynamic shared memory of one CTA
-int wave2_setup(const Wave2Variant& v, size_t smem_log);
-int wave2_launch(const Wave2Variant& v, bool boxes, bool log, const TraceArgs& a, int grid, size_t smem, cudaStream_t st);
 
 // trace_kernel<Rng, SW>: which = (xoshiro ? 2 : 0) + (more than 64 recorders ? 1 : 0)
 int reg_occupancy(int which, size_t smem, int* blocks_per_sm);

@@ -15,12 +15,10 @@ LIB_PATH = os.environ.get(
     "PVTRACE_B200_LIB", os.path.join(os.path.dirname(HERE), "csrc", "libpvtrace_b200.so"))
 
 FLAG_REGISTER_KERNEL = 1  # PVT_FLAG_REGISTER_KERNEL: force the one-photon-per-lane kernel
-FLAG_WARP_KERNEL = 2      # PVT_FLAG_WARP_KERNEL: warp_wavefront_kernel (autonomous warps)
-FLAG_CTA_KERNEL = 4       # PVT_FLAG_CTA_KERNEL: wavefront_kernel (two-stage CTA wavefront)
 RNG_PHILOX, RNG_XOSHIRO = 0, 1
 RNG_MODES = {"philox": RNG_PHILOX, "xoshiro": RNG_XOSHIRO}
 NSTATS = 32
-STAT_STEPS, STAT_RAYS, STAT_LAUNCHES, STAT_EVENTS = 0, 1, 2, 3
+STAT_STEPS, STAT_RAYS, STAT_LAUNCHES, STAT_EVENTS, STAT_H2D_BYTES = 0, 1, 2, 3, 4
 
 _P_I32, _P_F64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
 _P_I64, _P_U8 = C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
@@ -207,6 +205,8 @@ def load_library():
         "pvt_struct_sizes": (None, [C.POINTER(C.c_int32)]),
         "pvt_trace_bundle": (C.c_int, [C.POINTER(PvtScene), C.POINTER(PvtEmit), vp, vp, vp,
                                        C.POINTER(PvtParams), C.POINTER(PvtOut), _P_F64]),
+        "pvt_trace_bundle_devices": (C.c_int, [C.POINTER(PvtScene), C.POINTER(PvtEmit), vp, vp, vp,
+                                               C.POINTER(PvtParams), C.c_int32, _P_I32, C.POINTER(PvtOut), _P_F64]),
         "pvt_context_create": (C.c_int, [C.POINTER(PvtScene), C.POINTER(PvtEmit), C.c_int, C.POINTER(vp)]),
         "pvt_context_destroy": (C.c_int, [vp]),
         "pvt_context_reset": (C.c_int, [vp, vp]),
@@ -240,7 +240,7 @@ def load_library():
 
 
 EXPORTED_SYMBOLS = (
-    "pvt_version", "pvt_device_count", "pvt_last_error", "pvt_struct_sizes", "pvt_trace_bundle", "pvt_context_create",
+    "pvt_version", "pvt_device_count", "pvt_last_error", "pvt_struct_sizes", "pvt_trace_bundle", "pvt_trace_bundle_devices", "pvt_context_create",
     "pvt_context_destroy", "pvt_context_reset", "pvt_trace_device", "pvt_context_read",
     "pvt_context_pack_tallies", "pvt_context_unpack_tallies", "pvt_emit_device", "pvt_emit_bundle",
     "pvt_intersect_bundle", "pvt_intersect_device", "pvt_test_fresnel_reflectivity",
@@ -265,11 +265,13 @@ def _vp(array):
 
 def trace_bundle(compiled, positions, directions, wavelengths, seed, maxsteps, max_events, emit_method,
                  num_threads=0, record_every=1, *, emitter=None, n=None, first_index=0, rng_mode=RNG_PHILOX,
-                 device=0, return_elapsed=False, flags=0):
+                 device=0, return_elapsed=False, flags=0, devices=None):
     """Drop-in for pvtrace.engine._kernel.trace_bundle (pvtrace/engine/_kernel.pyx:903-1115).
 
     `num_threads` is accepted for signature compatibility and ignored (the device schedules itself).  With an
     `emitter` (CompiledEmitter) the three ray arrays may be None and `n` rays are sampled on the device.
+    `devices`: a sequence of CUDA ordinals to spread the bundle over (contiguous index slices, one host thread per
+    device inside the library, tallies summed); None or one entry: the single `device`.
     """
     lib = load_library()
     if positions is not None:
@@ -290,10 +292,19 @@ def trace_bundle(compiled, positions, directions, wavelengths, seed, maxsteps, m
                          flags)
     data, out = allocate_outputs(compiled, n, max_events, record_every)
     elapsed = C.c_double(0.0)
-    status = lib.pvt_trace_bundle(C.byref(scene), C.byref(emit_struct) if emit_struct is not None else None,
-                                  _vp(positions), _vp(directions), _vp(wavelengths), C.byref(params),
-                                  C.byref(out), C.byref(elapsed))
-    check(status, "pvt_trace_bundle")
+    emit_ref = C.byref(emit_struct) if emit_struct is not None else None
+    if devices is not None and len(devices) > 1:
+        ids = np.ascontiguousarray(devices, dtype=np.int32)
+        status = lib.pvt_trace_bundle_devices(C.byref(scene), emit_ref, _vp(positions), _vp(directions), _vp(wavelengths),
+                                              C.byref(params), len(ids), _as_ptr(ids, np.int32), C.byref(out),
+                                              C.byref(elapsed))
+        check(status, "pvt_trace_bundle_devices")
+    else:
+        if devices is not None and len(devices) == 1:
+            params.device = int(devices[0])
+        status = lib.pvt_trace_bundle(C.byref(scene), emit_ref, _vp(positions), _vp(directions), _vp(wavelengths),
+                                      C.byref(params), C.byref(out), C.byref(elapsed))
+        check(status, "pvt_trace_bundle")
     data = finalize_outputs(compiled, data, n, record_every)
     if return_elapsed:
         return data, elapsed.value

@@ -1,7 +1,8 @@
 """Python-facing API of the GPU engine: `simulate`, `simulate_stream`, `EngineResult`, `RecorderResult`.
 
 Signatures, result shapes and error behaviour follow pvtrace/engine/api.py:17-264.  Differences, all additive:
-keyword-only `rng`, `device`, `first_index`; initial rays are sampled on the device from the run's seed when every
+keyword-only `rng`, `device`, `devices`, `first_index`; `workers` -- OpenMP threads in the reference -- is the number of
+GPUs of this process to spread the bundle over (None: one); initial rays are sampled on the device from the run's seed when every
 light uses built-in delegates (the reference samples them with the unseeded global numpy RNG, emit.py:31-88);
 `elapsed` is the device time of the trace call measured with CUDA events; under an initialised
 `torch.distributed` process group `simulate` shards the photons over the ranks and all-reduces the tallies
@@ -73,17 +74,20 @@ class EngineResult:
     tallies over every ray, and an event log for every `record_every`-th ray where event k of recorded ray j is
     row `j * max_events + k`."""
 
-    def __init__(self, compiled, data, sources, max_events, record_every, elapsed):
+    def __init__(self, compiled, data, sources, max_events, record_every, elapsed, num_rays=None, first_index=0):
         self.compiled = compiled
         self.data = data
-        self.sources = sources
+        self.sources = sources  # light name per ray of THIS process's slice (all rays when not sharded)
         self.max_events = max_events
         self.record_every = record_every
         self.elapsed = elapsed
+        self.first_index = int(first_index)  # global index of the first ray of the slice (numbering of sinks)
+        self._num_rays = num_rays
 
     @property
     def num_rays(self):
-        return len(self.sources)
+        """Rays the tallies refer to: under a process group the GLOBAL count (the tallies are all-reduced)."""
+        return len(self.sources) if self._num_rays is None else int(self._num_rays)
 
     @property
     def num_recorded(self):
@@ -93,7 +97,7 @@ class EngineResult:
     def recorded_indices(self):
         if self.record_every <= 0:
             return np.zeros(0, dtype=np.int64)
-        return np.arange(0, self.num_rays, self.record_every, dtype=np.int64)
+        return np.arange(0, len(self.sources), self.record_every, dtype=np.int64)
 
     @property
     def stats(self):
@@ -155,7 +159,7 @@ class EngineResult:
             yield history
 
 
-def _to_sqlite(self, dbfilepath, first_throw_id=0, end_rays=False):
+def _to_sqlite(self, dbfilepath, first_throw_id=None, end_rays=False):
     """Write the logged histories into the reference CLI's database layout (engine/sinks.py)."""
     from pvtrace_b200.engine import sinks
 
@@ -166,12 +170,14 @@ EngineResult.to_sqlite = _to_sqlite
 
 
 def simulate(scene, num_rays, seed=None, workers=None, maxsteps=1000, max_events=128, emit_method="kT",
-             record_every=1, *, rng="philox", device=None, first_index=0):
+             record_every=1, *, rng="philox", device=None, devices=None, first_index=0):
     """Trace `num_rays` through `scene` on the GPU.
 
     Recorders attached to scene nodes tally every ray; full event histories are kept for every
     `record_every`-th ray (all when 1, none when 0).  Raises `UnsupportedSceneError` if the scene cannot be
-    flattened and `ValueError` for a bad `emit_method`.  `workers` belongs to the CPU engine and is ignored.
+    flattened and `ValueError` for a bad `emit_method`.  `workers` (threads of the reference's CPU engine) is the
+    number of GPUs to use: the first `workers` devices, or pass `devices=[...]` explicitly; the result does not depend
+    on it (ray i is a function of (seed, i, scene) alone).
     """
     if emit_method not in EMIT_METHODS:
         raise ValueError(f"emit_method must be one of {sorted(EMIT_METHODS)}")
@@ -187,6 +193,8 @@ def simulate(scene, num_rays, seed=None, workers=None, maxsteps=1000, max_events
         return distributed.simulate_sharded(scene, compiled, num_rays, int(seed), maxsteps, max_events, emit_method,
                                             record_every, rng=rng, first_index=first_index)
 
+    if devices is None and workers is not None and int(workers) > 1 and device is None:
+        devices = list(range(min(int(workers), max(_cuda.device_count(), 1))))
     emitter = compile_emitter(scene)
     if emitter is not None:
         positions = directions = wavelengths = None
@@ -196,8 +204,9 @@ def simulate(scene, num_rays, seed=None, workers=None, maxsteps=1000, max_events
     data, elapsed = _cuda.trace_bundle(
         compiled, positions, directions, wavelengths, int(seed), int(maxsteps), int(max_events),
         EMIT_METHODS[emit_method], 0, int(record_every), emitter=emitter, n=int(num_rays),
-        first_index=int(first_index), rng_mode=_cuda.RNG_MODES[rng], device=int(device or 0), return_elapsed=True)
-    return EngineResult(compiled, data, sources, max_events, record_every, elapsed)
+        first_index=int(first_index), rng_mode=_cuda.RNG_MODES[rng], device=int(device or 0), return_elapsed=True,
+        devices=devices)
+    return EngineResult(compiled, data, sources, max_events, record_every, elapsed, first_index=first_index)
 
 
 def simulate_stream(scene, num_rays, bundle=50000, seed=None, **kwargs):

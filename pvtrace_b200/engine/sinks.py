@@ -59,10 +59,14 @@ def end_ray_mask(kind, hit, container, adjacent):
     return keep
 
 
-def write_sqlite(result, dbfilepath, first_throw_id=0, end_rays=False, connection=None):
+def write_sqlite(result, dbfilepath, first_throw_id=None, end_rays=False, connection=None):
     """Append every logged (ray, event) pair of `result` to the database at `dbfilepath` (created with the schema if
-    it has no `ray` table yet).  Returns the number of pairs written.  `first_throw_id` lets bundles of
-    `simulate_stream` continue the numbering."""
+    it has no `ray` table yet).  Returns the number of pairs written.  `throw_id` is the index of the THROWN ray
+    (the reference CLI numbers every throw, logged or not): `first_throw_id` + the ray's index in the bundle, with
+    `first_throw_id` defaulting to the bundle's first global ray index, so bundles of `simulate_stream` continue the
+    numbering and `record_every > 1` leaves gaps instead of renumbering."""
+    if first_throw_id is None:
+        first_throw_id = int(getattr(result, "first_index", 0))
     own = connection is None
     if own:
         connection = sqlite3.connect(dbfilepath)
@@ -89,7 +93,7 @@ def write_sqlite(result, dbfilepath, first_throw_id=0, end_rays=False, connectio
     for k, (row, j) in enumerate(zip(rows.tolist(), throw.tolist())):
         src = int(d["source"][row])
         source = result.sources[int(recorded[j])] if src < 0 else comp_names[src]
-        ray_rows.append((first_throw_id + j, float(pos[row, 0]), float(pos[row, 1]), float(pos[row, 2]),
+        ray_rows.append((first_throw_id + int(recorded[j]), float(pos[row, 0]), float(pos[row, 1]), float(pos[row, 2]),
                          float(direc[row, 0]), float(direc[row, 1]), float(direc[row, 2]), float(d["wavelength"][row]),
                          source, float(d["travelled"][row]), float(d["duration"][row])))
         kind = int(d["kind"][row])

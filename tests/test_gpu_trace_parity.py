@@ -23,7 +23,7 @@ from pvtrace_b200.engine.compiler import EMIT_METHODS
 
 pytestmark = pytest.mark.gpu
 NAMES = list(configs.CONFIGS)
-KERNELS = {"default": 0, "warp": _cuda.FLAG_WARP_KERNEL, "cta": _cuda.FLAG_CTA_KERNEL, "register": _cuda.FLAG_REGISTER_KERNEL}
+KERNELS = {"wavefront": 0, "register": _cuda.FLAG_REGISTER_KERNEL}
 
 
 def _both(name, n, record_every, max_events=256, seed=7, rng_mode=_cuda.RNG_PHILOX, flags=0):

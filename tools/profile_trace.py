@@ -38,10 +38,3 @@ for rep in range(reps):
     elif prof.sum() > 0:  # library built with PVT_NVCC_FLAGS=-DPVT_PROFILE_STAGES: warp 0's cycles per stage, summed over CTAs
         extra = "  stage1/bar1/stage2/bar2 % of warp-0 time: " + " ".join(f"{100 * v / prof.sum():.1f}" for v in prof)
     print(f"{name} n={n} rep={rep} {ms:.3f} ms {n / ms / 1e3:.1f} Mphot/s steps/photon {d['stats'][0] / n:.3f}{extra}", flush=True)
-    w2 = d["stats"][8:20]
-    if w2.sum() > 0:  # library built with -DPVT_W2_STATS: chunks / lanes per queue (V S E F), cycles per phase of lane 0
-        names = "VSEF"
-        fill = " ".join(f"{names[k]}:{int(w2[k])}x{(w2[4 + k] / max(w2[k], 1)):.1f}" for k in range(4))
-        cyc = w2[8:12].astype(float)
-        print(f"   chunks x mean lanes {fill}; cycles % sched/interact/tally-or-fetch/classify: " +
-              " ".join(f"{100 * v / cyc.sum():.1f}" for v in cyc) + f"; cycles per chunk {cyc.sum() / max(w2[:4].sum(), 1):.0f}", flush=True)
