@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PVT_VERSION 100 /* 0.1.0 */
+#define PVT_VERSION 200 /* 0.2.0 */
 
 /* Compile-time limits shared with the reference kernel (_kernel.pyx:65-68, compiler.py:23). */
 #define PVT_MAX_NODES 128
@@ -76,7 +76,7 @@ typedef struct pvt_scene_t {
   int32_t n_hists;
   int32_t total_bins;
   int32_t n_facets;
-  int32_t reserved0;
+  int32_t n_refl_knots;  /* len(refl_x) == len(refl_y): wavelength-tabulated facet reflectivities */
 
   const int32_t* geom_type;        /* [n_nodes]      PVT_GEOM_*                                        */
   const double*  geom_params;      /* [n_nodes,4]    box: sx,sy,sz,- | sphere: r | cylinder: length,radius */
@@ -126,6 +126,14 @@ typedef struct pvt_scene_t {
   const double*  facet_atol;         /* [n_facets] per-component tolerance                             */
   const double*  facet_reflectivity; /* [n_facets] constant R in [0,1]; < 0 => Fresnel                 */
   const int32_t* facet_flags;        /* [n_facets] PVT_FACET_*                                         */
+  /* coatings (examples/006 Coatings.ipynb): a facet may cover only PART of a face -- the open box
+   * lo < p < hi of the node's local frame -- and its reflectivity may be a table over wavelength (linear
+   * interpolation, clamped to the end values and to [0,1]), which then replaces facet_reflectivity.      */
+  const double*  facet_region;       /* [n_facets,6] lo xyz, hi xyz (+-inf = unbounded); NULL => whole faces */
+  const int32_t* facet_refl_start;   /* [n_facets] into refl_x / refl_y; NULL => no tables              */
+  const int32_t* facet_refl_n;       /* [n_facets] knots, 0 => facet_reflectivity applies               */
+  const double*  refl_x;             /* [n_refl_knots] nanometres, ascending                            */
+  const double*  refl_y;             /* [n_refl_knots] reflectivity                                     */
 } pvt_scene_t;
 
 /* On-device emission of the built-in light delegates (pvtrace/light/light.py:48-157,
@@ -266,9 +274,13 @@ int pvt_emit_bundle(const pvt_emit_t* emit, double* positions, double* direction
 int pvt_intersect_bundle(const pvt_scene_t* scene, const double* positions, const double* directions,
                          int64_t n, double* t0, int32_t* hit, int32_t* container, int32_t* adjacent,
                          int device, double* elapsed_s);
-/* device-pointer variant for benchmarking against the HBM roofline (60 B/ray algorithmic) */
+/* device-pointer variants.  The packed form is the stage as SURVEY 8d counts it against the HBM roofline -- 60 B per
+ * ray: 48 in, t0 (8) + ONE word of ids (4) out, ids = hit | container << 8 | adjacent << 16 with 0xff for "none" (node
+ * indices are < PVT_MAX_NODES); the other writes the three int32 arrays of the host call (68 B per ray).          */
 int pvt_intersect_device(pvt_context_t* ctx, const double* d_positions, const double* d_directions, int64_t n,
                          double* d_t0, int32_t* d_hit, int32_t* d_container, int32_t* d_adjacent, void* stream);
+int pvt_intersect_device_packed(pvt_context_t* ctx, const double* d_positions, const double* d_directions, int64_t n,
+                                double* d_t0, uint32_t* d_ids, void* stream);
 
 /* ---------------------------------------------------------------- device math helpers (known-answer tests)
  * One thin kernel launch each; host pointers; `n` independent evaluations.  They expose the SAME device

@@ -451,16 +451,66 @@ static void nearest_surface(const pvt_scene_t* S, const double* pos, const doubl
 /* ------------------------------------------------------------------------------------------------
  * One photon, start to finish (_kernel.pyx:603-897; spec in SURVEY.md Appendix A).                     */
 
-static int find_facet(const pvt_scene_t* S, int node, const double* nl) {
+/* Facet extension (no counterpart in _kernel.pyx; lowers the SurfaceDelegate subclasses of pvtrace/device/lsc.py:22-86
+ * and examples/006 Coatings.ipynb cell 3 into data): first facet of `node` whose LOCAL normal equals nl within its
+ * tolerance and whose region -- an open box of the local frame, the whole space unless the coating is partial --
+ * holds the local point lp. */
+static int find_facet(const pvt_scene_t* S, int node, const double* nl, const double* lp) {
   if (S->n_facets <= 0 || !S->facet_count) return -1;
   int f0 = S->facet_start[node], f1 = f0 + S->facet_count[node];
   for (int f = f0; f < f1; ++f) {
     const double* fn = S->facet_normal + 3 * f;
     double tol = S->facet_atol[f];
-    if (fabs(fn[0] - nl[0]) <= tol && fabs(fn[1] - nl[1]) <= tol && fabs(fn[2] - nl[2]) <= tol) return f;
+    if (!(fabs(fn[0] - nl[0]) <= tol && fabs(fn[1] - nl[1]) <= tol && fabs(fn[2] - nl[2]) <= tol)) continue;
+    if (S->facet_region) {
+      const double* g = S->facet_region + 6 * f;
+      if (!(lp[0] > g[0] && lp[1] > g[1] && lp[2] > g[2] && lp[0] < g[3] && lp[1] < g[4] && lp[2] < g[5])) continue;
+    }
+    return f;
   }
   return -1;
 }
+
+/* What the surface of `hit` does to a ray that has just reached it at world point pos (:848-895 + the facet
+ * extension): local point, normals, incidence angle, reflectivity, and how to reflect / transmit. */
+typedef struct {
+  double lp[3], nl[3], nw[3], nf[3], angle, R, n1, n2;
+  int fresnel, straight, lambert;
+} surface_t;
+
+static void surface_setup(const pvt_scene_t* S, int hit, int container, int adjacent, const double* pos, const double* dir,
+                          double wl, surface_t* g) {
+  xform_point(S->world_to_local + 16 * hit, pos, g->lp);
+  primitive_normal(S->geom_type[hit], S->geom_params + 4 * hit, g->lp, g->nl);
+  xform_vector(S->local_to_world + 16 * hit, g->nl, g->nw);
+  for (int i = 0; i < 3; ++i) g->nf[i] = g->nw[i];
+  if (dot3(g->nf, dir) < 0.0) for (int i = 0; i < 3; ++i) g->nf[i] = -g->nf[i];
+  double c = dot3(g->nf, dir);
+  if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;
+  g->angle = acos(c);
+  g->fresnel = S->surface_type[hit] == PVT_SURF_FRESNEL;
+  g->n1 = S->refractive_index[container]; g->n2 = S->refractive_index[adjacent];
+  g->R = 0.0; g->straight = 0; g->lambert = 0;
+  int fixed = 0;
+  const int facet = find_facet(S, hit, g->nl, g->lp);
+  if (facet >= 0) {
+    g->straight = (S->facet_flags[facet] & PVT_FACET_TRANSMIT_STRAIGHT) != 0;
+    g->lambert = (S->facet_flags[facet] & PVT_FACET_REFLECT_LAMBERTIAN) != 0;
+    double fr = S->facet_reflectivity[facet];
+    if (S->facet_refl_n && S->refl_x && S->facet_refl_n[facet] > 0) { /* coating with a reflectivity spectrum */
+      int rs = S->facet_refl_start[facet];
+      fr = interp_clamped(wl, S->refl_x + rs, S->refl_y + rs, S->facet_refl_n[facet]);
+      fr = fr < 0.0 ? 0.0 : (fr > 1.0 ? 1.0 : fr);
+    }
+    if (fr >= 0.0) { g->R = fr; fixed = 1; }
+    /* where no refracted ray exists a facet that transmits by refraction reflects, whatever it states */
+    if (fixed && g->fresnel && !g->straight && g->n2 < g->n1 && sqrt(fmax(1.0 - c * c, 0.0)) * (g->n1 / g->n2) > 1.0) g->R = 1.0;
+  }
+  if (!fixed && g->fresnel) g->R = fresnel_R(g->angle, g->n1, g->n2);
+}
+
+/* direction after the reflect / transmit decision; (p1, p2) are the Lambertian uniforms */
+static void surface_apply(const surface_t* g, int reflected, const double* dir, double p1, double p2, double* out);
 
 /* Lambertian direction about unit vector n (basis chosen so that n = +z reproduces lambertian(), utils.py:173-186) */
 static void lambert_about(const double* n, double p1, double p2, double* out) {
@@ -477,6 +527,21 @@ static void lambert_about(const double* n, double p1, double p2, double* out) {
     t2[0] = b; t2[1] = 1.0 - n[1] * n[1] * a; t2[2] = -n[1];
   }
   for (int i = 0; i < 3; ++i) out[i] = loc[0] * t1[i] + loc[1] * t2[i] + loc[2] * n[i];
+}
+
+static void surface_apply(const surface_t* g, int reflected, const double* dir, double p1, double p2, double* out) {
+  if (reflected) {
+    if (g->lambert) {
+      double back[3] = {-g->nf[0], -g->nf[1], -g->nf[2]}; /* hemisphere the ray arrived from */
+      lambert_about(back, p1, p2, out);
+    } else {
+      mirror_dir(dir, g->nw, out);
+    }
+  } else if (g->fresnel && !g->straight) {
+    snell_dir(dir, g->nf, g->n1, g->n2, out);
+  } else {
+    out[0] = dir[0]; out[1] = dir[1]; out[2] = dir[2];
+  }
 }
 
 static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, acc_t* A, double* pos, double* dir,
@@ -615,51 +680,25 @@ static int trace_photon(const pvt_scene_t* S, const pvt_params_t* P, log_t* L, a
       log_event(L, PVT_EV_KILL, hit, container, -1, -1, source, pos, dir, NULL, wl, travelled, duration);
       break;
     }
-    double lp[3], nl[3], nw[3], nf[3];
-    xform_point(S->world_to_local + 16 * hit, pos, lp);
-    primitive_normal(S->geom_type[hit], S->geom_params + 4 * hit, lp, nl);
-    xform_vector(S->local_to_world + 16 * hit, nl, nw);
-    nf[0] = nw[0]; nf[1] = nw[1]; nf[2] = nw[2];
-    if (dot3(nf, dir) < 0.0) { nf[0] = -nf[0]; nf[1] = -nf[1]; nf[2] = -nf[2]; }
-    double c = dot3(nf, dir);
-    if (c > 1.0) c = 1.0; else if (c < -1.0) c = -1.0;
-    const double angle = acos(c);
-
-    const int fresnel = S->surface_type[hit] == PVT_SURF_FRESNEL;
-    const double n1 = S->refractive_index[container], n2 = S->refractive_index[adjacent];
-    double R = 0.0;
-    int straight = 0, lambert = 0;
-    const int facet = find_facet(S, hit, nl);
-    if (facet >= 0) {
-      straight = (S->facet_flags[facet] & PVT_FACET_TRANSMIT_STRAIGHT) != 0;
-      lambert = (S->facet_flags[facet] & PVT_FACET_REFLECT_LAMBERTIAN) != 0;
-    }
-    if (facet >= 0 && S->facet_reflectivity[facet] >= 0.0) R = S->facet_reflectivity[facet];
-    else if (fresnel) R = fresnel_R(angle, n1, n2);
-
+    surface_t g;
+    surface_setup(S, hit, container, adjacent, pos, dir, wl, &g);
     double u = 1.0;
-    if (R > 0.0) u = rng_draw(&rng, BLOCK_PATH, 1); /* surface.py:231-240: no draw when R == 0 */
+    if (g.R > 0.0) u = rng_draw(&rng, BLOCK_PATH, 1); /* surface.py:231-240: no draw when R == 0 */
     double nd[3];
-    if (u < R) {
-      if (lambert) {
-        double back[3] = {-nf[0], -nf[1], -nf[2]}; /* hemisphere the ray arrived from */
-        double p1 = rng_draw(&rng, BLOCK_LAMBERT, 0), p2 = rng_draw(&rng, BLOCK_LAMBERT, 1);
-        lambert_about(back, p1, p2, nd);
-      } else {
-        mirror_dir(dir, nw, nd);
-      }
+    if (u < g.R) {
+      double p1 = 0.0, p2 = 0.0;
+      if (g.lambert) { p1 = rng_draw(&rng, BLOCK_LAMBERT, 0); p2 = rng_draw(&rng, BLOCK_LAMBERT, 1); }
+      surface_apply(&g, 1, dir, p1, p2, nd);
       dir[0] = nd[0]; dir[1] = nd[1]; dir[2] = nd[2];
-      log_event(L, PVT_EV_REFLECT, hit, container, adjacent, -1, source, pos, dir, nw, wl, travelled, duration);
+      log_event(L, PVT_EV_REFLECT, hit, container, adjacent, -1, source, pos, dir, g.nw, wl, travelled, duration);
       if (have_rec && container != hit)
-        tally_event(S, A, PVT_REC_REFLECTED, hit, seen, nw, lp, angle, wl, travelled, duration);
+        tally_event(S, A, PVT_REC_REFLECTED, hit, seen, g.nw, g.lp, g.angle, wl, travelled, duration);
     } else {
-      if (fresnel && !straight) {
-        snell_dir(dir, nf, n1, n2, nd);
-        dir[0] = nd[0]; dir[1] = nd[1]; dir[2] = nd[2];
-      }
-      log_event(L, PVT_EV_TRANSMIT, hit, container, adjacent, -1, source, pos, dir, nw, wl, travelled, duration);
+      surface_apply(&g, 0, dir, 0.0, 0.0, nd);
+      dir[0] = nd[0]; dir[1] = nd[1]; dir[2] = nd[2];
+      log_event(L, PVT_EV_TRANSMIT, hit, container, adjacent, -1, source, pos, dir, g.nw, wl, travelled, duration);
       if (have_rec)
-        tally_event(S, A, container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING, hit, seen, nw, lp, angle, wl,
+        tally_event(S, A, container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING, hit, seen, g.nw, g.lp, g.angle, wl,
                     travelled, duration);
     }
   }
@@ -805,6 +844,23 @@ int pvt_oracle_intersect_bundle(const pvt_scene_t* S, const double* positions, c
     hit[i] = nh.nhits ? nh.hit : -1;
     container[i] = nh.container;
     adjacent[i] = nh.adjacent;
+  }
+  return 0;
+}
+
+/* One surface interaction on its own (pins the facet extension against the reference's SurfaceDelegate classes called
+ * directly, tests/test_reference_pins.py): `pos` lies on the surface of `hit`; out_R = reflectivity, out_reflect /
+ * out_transmit = the two candidate directions (Lambertian uniforms p1, p2). */
+int pvt_oracle_surface_event(const pvt_scene_t* S, int64_t n, const int32_t* hit, const int32_t* container,
+                             const int32_t* adjacent, const double* pos, const double* dir, const double* wl,
+                             const double* p1, const double* p2, double* out_R, double* out_reflect, double* out_transmit) {
+  for (int64_t i = 0; i < n; ++i) {
+    surface_t g;
+    surface_setup(S, hit[i], container[i], adjacent[i], pos + 3 * i, dir + 3 * i, wl[i], &g);
+    out_R[i] = g.R;
+    surface_apply(&g, 1, dir + 3 * i, p1 ? p1[i] : 0.5, p2 ? p2[i] : 0.5, out_reflect + 3 * i);
+    if (g.R < 1.0) surface_apply(&g, 0, dir + 3 * i, 0.0, 0.0, out_transmit + 3 * i);
+    else for (int k = 0; k < 3; ++k) out_transmit[3 * i + k] = NAN;
   }
   return 0;
 }

@@ -104,6 +104,26 @@ def intersect_bundle(compiled, positions, directions):
     return t0, hit, container, adjacent
 
 
+def surface_event(compiled, hit, container, adjacent, positions, directions, wavelengths, p1=None, p2=None):
+    """One surface interaction per row (points ON the surface of node `hit`): reflectivity, reflected direction and
+    transmitted direction (NaN where the reflectivity is 1) -- the facet / coating extension on its own."""
+    lib = load()
+    positions, directions, wavelengths = _f64(positions), _f64(directions), _f64(wavelengths)
+    n = len(wavelengths)
+    ids = [np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.int32), (n,))) for v in (hit, container, adjacent)]
+    p1 = None if p1 is None else _f64(p1)
+    p2 = None if p2 is None else _f64(p2)
+    scene, keep = abi.marshal_scene(compiled)
+    refl, r_dir, t_dir = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3))
+    vp = C.c_void_p
+    fn = lib.pvt_oracle_surface_event
+    fn.restype, fn.argtypes = C.c_int, [C.POINTER(abi.PvtScene), C.c_int64] + [vp] * 11
+    if fn(C.byref(scene), n, _vp(ids[0]), _vp(ids[1]), _vp(ids[2]), _vp(positions), _vp(directions), _vp(wavelengths),
+          _vp(p1), _vp(p2), _vp(refl), _vp(r_dir), _vp(t_dir)) != 0:
+        raise RuntimeError("pvt_oracle_surface_event failed")
+    return refl, r_dir, t_dir
+
+
 def _call_helper(name, argtypes, *args):
     fn = getattr(load(), name)
     fn.restype, fn.argtypes = C.c_int, argtypes

@@ -102,6 +102,16 @@ static int validate_scene(const pvt_scene_t* S) {
     if (S->rec_hist_start[r] < 0 || S->rec_hist_start[r] + S->rec_hist_n[r] > S->n_hists)
       return fail("recorder %d: histogram range out of bounds", r);
   }
+  if (S->n_facets > 0 && S->facet_count) {
+    for (int i = 0; i < S->n_nodes; ++i)
+      if (S->facet_start[i] < 0 || S->facet_count[i] < 0 || S->facet_start[i] + S->facet_count[i] > S->n_facets)
+        return fail("node %d: facet range out of bounds", i);
+    if (S->facet_refl_n && S->refl_x && S->refl_y)
+      for (int f = 0; f < S->n_facets; ++f)
+        if (S->facet_refl_n[f] < 0 || (S->facet_refl_n[f] > 0 && (S->facet_refl_start[f] < 0 ||
+                                                                 S->facet_refl_start[f] + S->facet_refl_n[f] > S->n_refl_knots)))
+          return fail("facet %d: reflectivity table out of bounds", f);
+  }
   for (int h = 0; h < S->n_hists; ++h) {
     const long long cells = (long long)S->hist_na[h] * (S->hist_prop_b[h] < 0 ? 1 : S->hist_nb[h]);
     if (S->hist_offset[h] < 0 || S->hist_offset[h] + cells > S->total_bins) return fail("histogram %d: bins out of bounds", h);
@@ -175,14 +185,6 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
     rc = fail("tally reset failed: %s", cudaGetErrorString(cudaGetLastError()));
   for (int which = 0; which < 4 && !rc; ++which) rc = reg_occupancy(which, c->smem_bytes, &c->blocks_per_sm[which]);
   if (!rc && c->wave_threads > 0) rc = wave_setup(WaveVariant{c->wave_threads, c->wave_pool, c->wave_ctas}, c->wave_smem);
-  if (!rc && c->smem_bytes > 48 * 1024 &&
-      (cudaFuncSetAttribute(intersect_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess ||
-       cudaFuncSetAttribute(intersect_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes) != cudaSuccess))
-    rc = fail("cudaFuncSetAttribute(intersect_kernel) failed");
   if (rc) {
     pvt_context_destroy(c);
     return rc;
@@ -403,17 +405,6 @@ extern "C" int pvt_context_unpack_tallies(pvt_context_t* c, void* stream) {
   return 0;
 }
 
-// resident CTAs of intersect_kernel (3 per SM by its launch bounds, fewer if shared memory says so)
-template <class K>
-static int intersect_grid(const pvt_context* c, long long n, K kernel) {
-  int per_sm = 3;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, c->smem_bytes);
-  if (per_sm < 1) per_sm = 1;
-  long long blocks = (n + 255) / 256;
-  const long long cap = (long long)c->sm_count * per_sm;
-  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
-}
-
 static int grid_for(long long n, int sm_count) {
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)sm_count * 8;
@@ -437,22 +428,17 @@ extern "C" int pvt_intersect_device(pvt_context_t* c, const double* d_pos, const
   if (!c) return fail("ctx is NULL");
   if (n <= 0) return 0;
   PVT_CUDA(cudaSetDevice(c->device));
-  int ctas = 3;  // 80 registers with one tile in flight: measured best (4.26 TB/s of 68 B/ray traffic on config 2)
-  if (const char* env = getenv("PVT_INTERSECT_CTAS")) ctas = atoi(env);
-#define PVT_INTERSECT_LAUNCH(K, BX)                                                                                  \
-  intersect_kernel<K, BX><<<intersect_grid(c, n, intersect_kernel<K, BX>), 256, c->smem_bytes, (cudaStream_t)stream>>>( \
-      c->hdr, c->blob.ptr, c->blob_words, c->scene_in_smem, d_pos, d_dir, n, d_t0, d_hit, d_container, d_adjacent)
-  if (c->wave_boxes) {
-    if (ctas <= 2) PVT_INTERSECT_LAUNCH(2, true);
-    else if (ctas == 3) PVT_INTERSECT_LAUNCH(3, true);
-    else PVT_INTERSECT_LAUNCH(4, true);
-  } else {
-    if (ctas <= 2) PVT_INTERSECT_LAUNCH(2, false);
-    else if (ctas == 3) PVT_INTERSECT_LAUNCH(3, false);
-    else PVT_INTERSECT_LAUNCH(4, false);
-  }
-  PVT_CUDA(cudaGetLastError());
-  return 0;
+  return intersect_launch(c->wave_boxes, false, c->hdr, c->blob.ptr, d_pos, d_dir, n, d_t0, nullptr, d_hit, d_container,
+                          d_adjacent, c->sm_count, (cudaStream_t)stream);
+}
+
+extern "C" int pvt_intersect_device_packed(pvt_context_t* c, const double* d_pos, const double* d_dir, int64_t n, double* d_t0,
+                                           uint32_t* d_ids, void* stream) {
+  if (!c) return fail("ctx is NULL");
+  if (n <= 0) return 0;
+  PVT_CUDA(cudaSetDevice(c->device));
+  return intersect_launch(c->wave_boxes, true, c->hdr, c->blob.ptr, d_pos, d_dir, n, d_t0, d_ids, nullptr, nullptr, nullptr,
+                          c->sm_count, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------

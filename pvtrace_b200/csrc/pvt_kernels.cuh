@@ -884,70 +884,134 @@ __global__ void __launch_bounds__(kTraceThreads) trace_kernel(const __grid_const
 }
 
 // ---- the intersect stage on its own ----------------------------------------------------------------------
-// 60 B of algorithmic traffic per ray: reads position + direction (48 B), writes t0 (8 B) and three int32 ids
-// (12 B; SURVEY 8d counts them packed as 4 B).  Every warp walks tiles of 32 rays: the tile's 96 + 96 input words
-// are fetched with fully coalesced loads (lane l takes words l, l + 32, l + 64 -- a ray's three words are NOT
-// loaded by its own lane, which would touch every sector three times), passed through shared memory, and the next
-// tile's loads are in flight while this one is intersected.  Streaming loads and stores: every byte is touched once.
-constexpr int kIntersectDepth = 1;  // tiles in flight per warp beyond the one being intersected (3 at 2 CTAs/SM measured slower: 0.62 vs 0.65 of peak)
-template <int kMinCtas, bool kBoxes>
-__global__ void __launch_bounds__(256, kMinCtas) intersect_kernel(const __grid_constant__ Header hdr, const double* blob,
-                                                           int blob_words, int scene_in_smem, const double* pos,
-                                                           const double* dir, long long n, double* t0, int32_t* hit,
-                                                           int32_t* container, int32_t* adjacent) {
-  constexpr int D = kIntersectDepth;
+// next_hit + find_container over a ray array (photon_tracer.py:26-109 == _kernel.pyx:666-714).  Algorithmic traffic
+// per ray: position + direction in (48 B), t0 (8 B) and the three node ids packed into one word (4 B) out
+// = 60 B; the unpacked form of the C ABI writes three int32 arrays instead (68 B).
+//
+// intersect_ring_kernel: persistent CTAs walk tiles of THREADS rays.  A tile's 2 x 24 THREADS bytes are fetched by
+// TWO bulk async copies (cp.async.bulk -> SASS UBLKCP, the TMA engine's 1-D path) into a ring of STAGES tiles in
+// shared memory, each stage with its own mbarrier: the copies of the next STAGES - 1 tiles are in flight while one
+// is intersected, no register holds data in flight, and a thread reads ITS ray's six words from shared memory
+// (stride 3 doubles: conflict free) -- the coalescing is the copy engine's business.  Only the node records of the
+// blob are staged (header + nodes: the stage touches nothing else).  Streaming stores: every byte is written once.
+__host__ __device__ constexpr int intersect_node_words(int n_nodes) { return kHeaderWords + n_nodes * kNodeWords; }
+__host__ __device__ constexpr size_t intersect_ring_smem(int n_nodes, int threads, int stages) {
+  return 16 + 8 * (size_t)stages + 8 /*pad to 16*/ + (size_t)intersect_node_words(n_nodes) * 8 + (size_t)stages * threads * 48;
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar_a, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar_a), "r"(parity)
+        : "memory");
+  }
+}
+
+// (a node id that is "none" is -1, whose low byte is the 0xff of the packed form; with no hit at all, hit and container
+// are -1 and t0 is the +inf the reduction started from)
+__device__ __forceinline__ uint32_t pack_ids(const Nearest& nh) {
+  const uint32_t lo = __byte_perm((uint32_t)nh.hit, (uint32_t)nh.container, 0x0040);  // bytes: hit, container, 0, 0 (of hit: byte 0 again)
+  return (lo & 0xffffu) | (((uint32_t)nh.adjacent & 0xffu) << 16);
+}
+
+template <bool kPacked>
+__device__ __forceinline__ void store_hit(const Nearest& nh, long long i, double* t0, uint32_t* packed, int32_t* hit,
+                                          int32_t* container, int32_t* adjacent) {
+  __stcs(t0 + i, nh.t0);
+  if (kPacked) {
+    __stcs(packed + i, pack_ids(nh));
+  } else {
+    __stcs(hit + i, nh.hit);
+    __stcs(container + i, nh.container);
+    __stcs(adjacent + i, nh.adjacent);
+  }
+}
+
+template <int THREADS, int STAGES, int kMinCtas, bool kBoxes, bool kPacked>
+__global__ void __launch_bounds__(THREADS, kMinCtas)
+    intersect_ring_kernel(const __grid_constant__ Header hdr, const double* blob, const double* pos, const double* dir,
+                          long long n, double* t0, uint32_t* packed, int32_t* hit, int32_t* container, int32_t* adjacent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ double tiles[8][192];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  double* sblob = reinterpret_cast<double*>(smem_raw + 16);
-  if (scene_in_smem) stage_blob(sblob, blob, (uint32_t)blob_words * 8u, bar);
-  const SceneView sv{scene_in_smem ? sblob : blob, &hdr};
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* tile = tiles[warp];
-  const long long stride = (long long)gridDim.x * 256, words = 3 * n;
-  long long base = (long long)blockIdx.x * 256 + warp * 32;  // first ray of this warp's tile
-  if (base >= n) return;
-  double in[D][6];
+  uint64_t* bar0 = reinterpret_cast<uint64_t*>(smem_raw);           // scene staging
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 16);      // [STAGES]
+  const int node_words = intersect_node_words(hdr.n_nodes);
+  double* sblob = reinterpret_cast<double*>(smem_raw + 16 + 8 * STAGES + 8 * (STAGES & 1));
+  double* ring = sblob + node_words;  // [STAGES][pos 3 THREADS | dir 3 THREADS]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < D; ++s) {
-    const long long tb = base + s * stride;
+    for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(full + s)));
+  }
+  stage_blob(sblob, blob, (uint32_t)node_words * 8u, bar0);  // (its barrier also publishes the inits above)
+  const SceneView sv{sblob, &hdr};
+
+  const long long tiles = n / THREADS;  // whole tiles go through the ring, the rest through plain loads below
+  constexpr uint32_t kTileBytes = THREADS * 24u;
+  auto issue = [&](long long tile, int s) {  // thread 0: both copies of `tile` into stage s
+    const uint32_t bar_a = smem_addr(full + s), dst = smem_addr(ring + (size_t)s * THREADS * 6);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(2u * kTileBytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(pos + tile * THREADS * 3), "r"(kTileBytes), "r"(bar_a) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + kTileBytes),
+                 "l"(dir + tile * THREADS * 3), "r"(kTileBytes), "r"(bar_a) : "memory");
+  };
+  if (tid == 0) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const long long w = 3 * tb + lane + 32 * k;
-      const bool ok = tb < n && w < words;
-      in[s][k] = ok ? __ldcs(pos + w) : 0.0;
-      in[s][3 + k] = ok ? __ldcs(dir + w) : 0.0;
+    for (int s = 0; s < STAGES; ++s) {
+      const long long tile = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (tile < tiles) issue(tile, s);
     }
   }
-  for (;;) {
-#pragma unroll
-    for (int s = 0; s < D; ++s) {  // unrolled: the D register sets rotate without moves
-      if (base >= n) return;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { tile[lane + 32 * k] = in[s][k]; tile[96 + lane + 32 * k] = in[s][3 + k]; }
-      __syncwarp();
-      const long long ahead = base + D * stride;
-      if (ahead < n) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const long long w = 3 * ahead + lane + 32 * k;
-          in[s][k] = w < words ? __ldcs(pos + w) : 0.0;
-          in[s][3 + k] = w < words ? __ldcs(dir + w) : 0.0;
-        }
+  int s = 0;
+  uint32_t parity = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    mbar_wait(smem_addr(full + s), parity);
+    const double* r = ring + (size_t)s * THREADS * 6;
+    const V3 p = V3{r[3 * tid], r[3 * tid + 1], r[3 * tid + 2]};
+    const V3 d = V3{r[THREADS * 3 + 3 * tid], r[THREADS * 3 + 3 * tid + 1], r[THREADS * 3 + 3 * tid + 2]};
+    __syncthreads();  // every thread has its ray: the stage may be refilled
+    if (tid == 0) {
+      const long long next = tile + (long long)STAGES * gridDim.x;
+      if (next < tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before the async-proxy write
+        issue(next, s);
       }
-      const long long i = base + lane;
-      const V3 p = V3{tile[3 * lane], tile[3 * lane + 1], tile[3 * lane + 2]};
-      const V3 d = V3{tile[96 + 3 * lane], tile[96 + 3 * lane + 1], tile[96 + 3 * lane + 2]};
-      __syncwarp();  // the tile may be overwritten from here on
-      if (i < n) {
-        const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
-        __stcs(t0 + i, nh.total ? nh.t0 : PVT_INF);
-        __stcs(hit + i, nh.total ? nh.hit : -1);
-        __stcs(container + i, nh.container);
-        __stcs(adjacent + i, nh.adjacent);
-      }
-      base += stride;
     }
+    const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
+    store_hit<kPacked>(nh, tile * THREADS + tid, t0, packed, hit, container, adjacent);
+    if (++s == STAGES) { s = 0; parity ^= 1u; }
+  }
+  // the last n % THREADS rays (a bulk copy moves multiples of 16 bytes from 16-byte aligned addresses only)
+  if (blockIdx.x == (unsigned)(tiles % gridDim.x)) {
+    const long long i = tiles * THREADS + tid;
+    if (i < n) {
+      const V3 p = V3{__ldcs(pos + 3 * i), __ldcs(pos + 3 * i + 1), __ldcs(pos + 3 * i + 2)};
+      const V3 d = V3{__ldcs(dir + 3 * i), __ldcs(dir + 3 * i + 1), __ldcs(dir + 3 * i + 2)};
+      const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
+      store_hit<kPacked>(nh, i, t0, packed, hit, container, adjacent);
+    }
+  }
+}
+
+// Plain-load form for ray arrays that are not 16-byte aligned (a bulk copy cannot start there) and for scenes whose
+// node records do not fit beside the ring: one ray per thread, grid-stride.
+template <bool kBoxes, bool kPacked>
+__global__ void __launch_bounds__(256) intersect_plain_kernel(const __grid_constant__ Header hdr, const double* blob,
+                                                              const double* pos, const double* dir, long long n, double* t0,
+                                                              uint32_t* packed, int32_t* hit, int32_t* container,
+                                                              int32_t* adjacent) {
+  const SceneView sv{blob, &hdr};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const V3 p = V3{__ldcs(pos + 3 * i), __ldcs(pos + 3 * i + 1), __ldcs(pos + 3 * i + 2)};
+    const V3 d = V3{__ldcs(dir + 3 * i), __ldcs(dir + 3 * i + 1), __ldcs(dir + 3 * i + 2)};
+    const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
+    store_hit<kPacked>(nh, i, t0, packed, hit, container, adjacent);
   }
 }
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 namespace pvt {
 
@@ -19,6 +20,13 @@ int wave_setup(const WaveVariant& v, size_t smem);
 int wave_service_threads();
 int wave_launch(const WaveVariant& v, int service, bool boxes, bool log, const TraceArgs& a, int grid, size_t smem,
                 cudaStream_t st);
+
+// the intersect stage on its own: ring of bulk copies when the arrays are 16-byte aligned, plain loads otherwise.
+// packed: node ids as one word per ray (hit | container << 8 | adjacent << 16, 0xff = none) into `ids`; else three int32 arrays
+struct Header;
+int intersect_launch(bool boxes, bool packed, const Header& hdr, const double* blob, const double* pos, const double* dir,
+                     long long n, double* t0, uint32_t* ids, int32_t* hit, int32_t* container, int32_t* adjacent,
+                     int sm_count, cudaStream_t st);
 
 // trace_kernel<Rng, SW>: which = (xoshiro ? 2 : 0) + (more than 64 recorders ? 1 : 0)
 int reg_occupancy(int which, size_t smem, int* blocks_per_sm);

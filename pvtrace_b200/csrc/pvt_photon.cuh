@@ -369,14 +369,18 @@ __device__ __forceinline__ void tally(const SceneView& sv, const TallySink& T, P
   for (int k = 0; k < SW; ++k) ph.seen[k] = seen.w[k];
 }
 
-// facet-surface extension: first facet of `node` whose LOCAL normal equals nl within its tolerance
-__device__ __forceinline__ int find_facet(const SceneView& sv, int node, const V3& nl) {
+// facet-surface extension: first facet of `node` whose LOCAL normal equals nl within its tolerance and whose region
+// (an open box of the local frame; the whole space unless the facet is a partial coating) holds the local point
+__device__ __forceinline__ int find_facet(const SceneView& sv, int node, const V3& nl, const V3& lp) {
   if (sv.hdr().n_facets <= 0) return -1;
   const int f0 = sv.node_int(node, NI_FACET_START), f1 = f0 + sv.node_int(node, NI_FACET_COUNT);
   for (int f = f0; f < f1; ++f) {
     const double* q = sv.facet(f);
     const double tol = q[kFacetAtol];
-    if (fabs(q[0] - nl.x) <= tol && fabs(q[1] - nl.y) <= tol && fabs(q[2] - nl.z) <= tol) return f;
+    if (fabs(q[0] - nl.x) <= tol && fabs(q[1] - nl.y) <= tol && fabs(q[2] - nl.z) <= tol &&
+        lp.x > q[kFacetRegion] && lp.y > q[kFacetRegion + 1] && lp.z > q[kFacetRegion + 2] &&
+        lp.x < q[kFacetRegion + 3] && lp.y < q[kFacetRegion + 4] && lp.z < q[kFacetRegion + 5])
+      return f;
   }
   return -1;
 }
@@ -605,13 +609,23 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
   const double n2 = sv.node(adjacent)[kNodeIndex];
   double R = 0.0;
   bool straight = false, lambert = false, fixed_R = false;
-  const int facet = find_facet(sv, hit, nl);
+  const int facet = find_facet(sv, hit, nl, lp);
   if (facet >= 0) {
     const int flags = sv.facet_flags(facet);
     straight = (flags & PVT_FACET_TRANSMIT_STRAIGHT) != 0;
     lambert = (flags & PVT_FACET_REFLECT_LAMBERTIAN) != 0;
-    const double fr = sv.facet(facet)[kFacetRefl];
+    double fr = sv.facet(facet)[kFacetRefl];
+    const int rn = sv.facet_refl_n(facet);
+    if (rn > 0) {  // coating with a reflectivity spectrum
+      const int rs = sv.facet_refl_start(facet);
+      fr = interp(ph.wl, sv.w + sv.hdr().off_refl_x + rs, sv.w + sv.hdr().off_refl_y + rs, rn);
+      fr = fr < 0.0 ? 0.0 : (fr > 1.0 ? 1.0 : fr);
+    }
     if (fr >= 0.0) { R = fr; fixed_R = true; }
+    // a coating does not repeal Snell's law: where no refracted ray exists (total internal reflection) a facet that
+    // transmits by refraction reflects, whatever reflectivity it states (the square root in snell() would be of a
+    // negative number)
+    if (fixed_R && fresnel && !straight && n2 < n1 && sqrt(fmax(1.0 - c * c, 0.0)) * (n1 / n2) > 1.0) R = 1.0;
   }
   if (!fixed_R && fresnel) R = fresnel_R_cos(c, n1, n2);
 

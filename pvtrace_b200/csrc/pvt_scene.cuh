@@ -23,6 +23,7 @@
 //               test against the face's world normal is done once here instead of per event; count < 0 marks a
 //               node whose faces cannot be pre-resolved (not a box, or a facet within 1e-9 of its tolerance)
 //   face_list   int32 recorder indices
+//   refl_x, refl_y  knots of the wavelength-tabulated facet reflectivities (coatings)
 //   ems_guide   per emitting component, kGuideBuckets + 1 uint16: guide[b] = last knot i with ems_cdf[i] <= b / kGuideBuckets
 //               (0 if none), so the inverse-CDF lookup bisects a bracket of a knot or two instead of the whole table
 #pragma once
@@ -39,7 +40,7 @@ struct Header {
   int32_t n_nodes, root_id, n_components, n_recorders, n_hists, total_bins, n_facets, n_lights;
   int32_t off_nodes, off_comps, off_abs_x, off_abs_y, off_ems_x, off_ems_cdf, off_recs, off_hists;
   int32_t off_facets, off_lights, off_wl_x, off_wl_cdf, total_words, off_rec_index, off_rec_list, off_face_index;
-  int32_t off_face_list, off_ems_guide, pad4, pad5;
+  int32_t off_face_list, off_ems_guide, off_refl_x, off_refl_y;
 };
 constexpr int kHeaderWords = sizeof(Header) / 8;
 static_assert(sizeof(Header) % 16 == 0, "header must keep 16-byte alignment for the bulk copy");
@@ -59,8 +60,8 @@ constexpr int kCompQy = 0, kCompTauRad = 1, kCompTauNr = 2, kCompPhaseParam = 3,
 constexpr int kRecFacet = 0, kRecAtol = 3, kRecInts = 4, kRecWords = 8;
 // histogram record: lo_a, hi_a, lo_b, hi_b | ints: prop_a,prop_b | na,nb | offset,pad | pad
 constexpr int kHistLoA = 0, kHistHiA = 1, kHistLoB = 2, kHistHiB = 3, kHistInts = 4, kHistWords = 8;
-// facet record: normal xyz, atol, reflectivity | ints: flags,pad | pad pad
-constexpr int kFacetNormal = 0, kFacetAtol = 3, kFacetRefl = 4, kFacetInts = 5, kFacetWords = 8;
+// facet record: normal xyz, atol, reflectivity | ints: flags,pad | ints: refl_start,refl_n | pad | region lo xyz, hi xyz | pad pad
+constexpr int kFacetNormal = 0, kFacetAtol = 3, kFacetRefl = 4, kFacetInts = 5, kFacetRegion = 8, kFacetWords = 16;
 // light record: l2w rows 0-2 (12) | pos_param (3) | dir_param | wl_param | ints: pos_kind,dir_kind | wl_kind,wl_start | wl_n,pad
 constexpr int kRecSelectors = 8;  // PVT_REC_* selectors 0..6, padded to 8
 constexpr int kLightL2W = 0, kLightPos = 12, kLightDir = 15, kLightWl = 16, kLightInts = 17, kLightSinDir = 20 /* sin(dir_param) */,
@@ -110,6 +111,9 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
   // worst case every recorder of a node matches all six faces
   h.off_face_list = w; w += (6 * S.n_recorders + 1) / 2;
   h.off_ems_guide = w; w += (S.n_components * (kGuideBuckets + 1) + 3) / 4;
+  const int n_refl = (h.n_facets && S.facet_refl_n && S.refl_x && S.refl_y) ? S.n_refl_knots : 0;
+  h.off_refl_x = w;  w += n_refl;
+  h.off_refl_y = w;  w += n_refl;
   w = (w + 1) & ~1;
   h.total_words = w;
 
@@ -189,6 +193,14 @@ inline std::vector<double> pack_scene(const pvt_scene_t& S, const pvt_emit_t* E)
     q[0] = S.facet_normal[3 * f]; q[1] = S.facet_normal[3 * f + 1]; q[2] = S.facet_normal[3 * f + 2];
     q[kFacetAtol] = S.facet_atol[f]; q[kFacetRefl] = S.facet_reflectivity[f];
     put_ints(blob, h.off_facets + (size_t)f * kFacetWords + kFacetInts, S.facet_flags[f], 0);
+    put_ints(blob, h.off_facets + (size_t)f * kFacetWords + kFacetInts + 1, n_refl ? S.facet_refl_start[f] : 0,
+             n_refl ? S.facet_refl_n[f] : 0);
+    for (int k = 0; k < 6; ++k)
+      q[kFacetRegion + k] = S.facet_region ? S.facet_region[6 * f + k] : (k < 3 ? -HUGE_VAL : HUGE_VAL);
+  }
+  if (n_refl) {
+    memcpy(&blob[h.off_refl_x], S.refl_x, n_refl * sizeof(double));
+    memcpy(&blob[h.off_refl_y], S.refl_y, n_refl * sizeof(double));
   }
   for (int l = 0; l < h.n_lights; ++l) {
     double* q = &blob[h.off_lights + (size_t)l * kLightWords];
@@ -281,6 +293,8 @@ struct SceneView {
   __device__ __forceinline__ int hist_int(int h, int k) const { return ival(hdr().off_hists + h * kHistWords + kHistInts + (k >> 1), k & 1); }
   __device__ __forceinline__ const double* facet(int f) const { return w + hdr().off_facets + f * kFacetWords; }
   __device__ __forceinline__ int facet_flags(int f) const { return ival(hdr().off_facets + f * kFacetWords + kFacetInts, 0); }
+  __device__ __forceinline__ int facet_refl_start(int f) const { return ival(hdr().off_facets + f * kFacetWords + kFacetInts + 1, 0); }
+  __device__ __forceinline__ int facet_refl_n(int f) const { return ival(hdr().off_facets + f * kFacetWords + kFacetInts + 1, 1); }
   // recorders attached to (node, selector): rec_candidate(start + k), k < count
   __device__ __forceinline__ void rec_range(int node, int sel, int& start, int& count) const {
     const int word = hdr().off_rec_index + node * kRecSelectors + sel;

@@ -24,7 +24,7 @@ _P_I32, _P_F64 = C.POINTER(C.c_int32), C.POINTER(C.c_double)
 _P_I64, _P_U8 = C.POINTER(C.c_int64), C.POINTER(C.c_uint8)
 
 _SCENE_COUNTS = ("n_nodes", "root_id", "n_components", "n_abs_knots", "n_ems_knots", "n_recorders", "n_hists",
-                 "total_bins", "n_facets", "reserved0")
+                 "total_bins", "n_facets", "n_refl_knots")
 # (struct field, CompiledScene attribute, dtype) in header order
 _SCENE_TABLES = (
     ("geom_type", "geom_type", np.int32), ("geom_params", "geom_params", np.float64),
@@ -49,6 +49,8 @@ _SCENE_TABLES = (
     ("facet_start", "facet_start", np.int32), ("facet_count", "facet_count", np.int32),
     ("facet_normal", "facet_normal", np.float64), ("facet_atol", "facet_atol", np.float64),
     ("facet_reflectivity", "facet_reflectivity", np.float64), ("facet_flags", "facet_flags", np.int32),
+    ("facet_region", "facet_region", np.float64), ("facet_refl_start", "facet_refl_start", np.int32),
+    ("facet_refl_n", "facet_refl_n", np.int32), ("refl_x", "refl_x", np.float64), ("refl_y", "refl_y", np.float64),
 )
 
 
@@ -102,9 +104,14 @@ def marshal_scene(compiled):
     s, keep = PvtScene(), []
     for field, attr, dtype in _SCENE_TABLES:
         value = getattr(compiled, attr, None)
-        if value is None:  # reference CompiledScene objects have no facet tables
+        if value is None:  # reference CompiledScene objects have no facet tables, older ones no coatings
+            n_facets = int(getattr(compiled, "n_facets", 0))
             if field in ("facet_start", "facet_count"):
                 value = np.zeros(len(compiled.geom_type), dtype=np.int32)
+            elif field == "facet_region":
+                value = np.tile(np.array([-np.inf] * 3 + [np.inf] * 3), (n_facets, 1))
+            elif field in ("facet_refl_start", "facet_refl_n"):
+                value = np.zeros(n_facets, dtype=np.int32)
             else:
                 value = np.zeros(0, dtype=dtype)
         arr = np.ascontiguousarray(value, dtype=dtype)
@@ -119,6 +126,7 @@ def marshal_scene(compiled):
     s.n_hists = len(compiled.hist_offset)
     s.total_bins = int(compiled.total_bins)
     s.n_facets = int(getattr(compiled, "n_facets", 0))
+    s.n_refl_knots = len(getattr(compiled, "refl_x", ()))
     return s, keep
 
 
@@ -218,6 +226,7 @@ def load_library():
         "pvt_emit_bundle": (C.c_int, [C.POINTER(PvtEmit), vp, vp, vp, C.c_int64, C.c_int64, C.c_uint64, C.c_int]),
         "pvt_intersect_bundle": (C.c_int, [C.POINTER(PvtScene), vp, vp, C.c_int64, vp, vp, vp, vp, C.c_int, _P_F64]),
         "pvt_intersect_device": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]),
+        "pvt_intersect_device_packed": (C.c_int, [vp, vp, vp, C.c_int64, vp, vp, vp]),
         "pvt_test_fresnel_reflectivity": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_int]),
         "pvt_test_specular_reflect": (C.c_int, [C.c_int64, vp, vp, vp, C.c_int]),
         "pvt_test_fresnel_refract": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, C.c_int]),
@@ -243,7 +252,7 @@ EXPORTED_SYMBOLS = (
     "pvt_version", "pvt_device_count", "pvt_last_error", "pvt_struct_sizes", "pvt_trace_bundle", "pvt_trace_bundle_devices", "pvt_context_create",
     "pvt_context_destroy", "pvt_context_reset", "pvt_trace_device", "pvt_context_read",
     "pvt_context_pack_tallies", "pvt_context_unpack_tallies", "pvt_emit_device", "pvt_emit_bundle",
-    "pvt_intersect_bundle", "pvt_intersect_device", "pvt_test_fresnel_reflectivity",
+    "pvt_intersect_bundle", "pvt_intersect_device", "pvt_intersect_device_packed", "pvt_test_fresnel_reflectivity",
     "pvt_test_specular_reflect", "pvt_test_fresnel_refract", "pvt_test_intersect", "pvt_test_local_normal",
     "pvt_test_interp", "pvt_test_rng_uniform", "pvt_test_sample_phase",
 )
@@ -383,6 +392,12 @@ class Context:
                                            C.c_void_p(d_wavelengths), int(n), int(first_index),
                                            int(seed) & 0xFFFFFFFFFFFFFFFF, C.c_void_p(stream))
         check(status, "pvt_emit_device")
+
+    def intersect_packed(self, d_positions, d_directions, n, d_t0, d_ids, stream=0):
+        """The intersect stage with the ids of a ray in one uint32 (hit | container << 8 | adjacent << 16, 0xff = none)."""
+        status = self._lib.pvt_intersect_device_packed(self._handle, C.c_void_p(d_positions), C.c_void_p(d_directions),
+                                                       int(n), C.c_void_p(d_t0), C.c_void_p(d_ids), C.c_void_p(stream))
+        check(status, "pvt_intersect_device_packed")
 
     def intersect(self, d_positions, d_directions, n, d_t0, d_hit, d_container, d_adjacent, stream=0):
         status = self._lib.pvt_intersect_device(self._handle, C.c_void_p(d_positions), C.c_void_p(d_directions), int(n),

@@ -131,7 +131,8 @@ class CompiledScene:
         absorb, emit = _SpectrumPool(), _SpectrumPool()
         columns = {k: [] for k in ("type", "qy", "tau_rad", "tau_nr", "phase_type", "phase_param",
                                    "abs_start", "abs_n", "ems_start", "ems_n")}
-        facets = {k: [] for k in ("normal", "atol", "reflectivity", "flags")}
+        facets = {k: [] for k in ("normal", "atol", "reflectivity", "flags", "region", "refl_start", "refl_n")}
+        facets["spectra"] = _SpectrumPool()
 
         for i, node in enumerate(nodes):
             material = node.geometry.material
@@ -163,6 +164,10 @@ class CompiledScene:
         self.facet_atol = _f64(facets["atol"])
         self.facet_reflectivity = _f64(facets["reflectivity"])
         self.facet_flags = _i32(facets["flags"])
+        self.facet_region = _f64(facets["region"]).reshape(-1, 6)
+        self.facet_refl_start = _i32(facets["refl_start"])
+        self.facet_refl_n = _i32(facets["refl_n"])
+        self.refl_x, self.refl_y = _f64(facets["spectra"].x), _f64(facets["spectra"].y)
 
     def _lower_surface(self, node, material, index, facets):
         delegate = material.surface.delegate
@@ -174,6 +179,13 @@ class CompiledScene:
                 facets["reflectivity"].append(-1.0 if facet.reflectivity is None else facet.reflectivity)
                 facets["flags"].append((FACET_TRANSMIT_STRAIGHT if facet.transmit == "straight" else 0)
                                        | (FACET_REFLECT_LAMBERTIAN if facet.reflect == "lambertian" else 0))
+                facets["region"].append(tuple(facet.region[0]) + tuple(facet.region[1]))
+                if facet.spectrum is not None:
+                    start, n = facets["spectra"].add(facet.spectrum[0], facet.spectrum[1])
+                else:
+                    start, n = 0, 0
+                facets["refl_start"].append(start)
+                facets["refl_n"].append(n)
             self.facet_count[index] = len(facets["atol"]) - self.facet_start[index]
             return SURF_FRESNEL
         if type(delegate) is FresnelSurfaceDelegate:

@@ -69,24 +69,63 @@ class FresnelSurfaceDelegate(SurfaceDelegate):
 class Facet(object):
     """Optical override for the part of a surface whose LOCAL outward normal equals `normal`.
 
-    reflectivity: None keeps Fresnel; a number in [0, 1] replaces it (1 = mirror, 0 = no reflection).
+    reflectivity: None keeps Fresnel; a number in [0, 1] replaces it (1 = mirror, 0 = no reflection); an (n, 2) array of
+                  (wavelength in nm, reflectivity) knots is a coating with a spectrum (linear interpolation, clamped to
+                  the end values).
     transmit:     "refract" (Snell) or "straight" (index matched: direction unchanged).
     reflect:      "specular" or "lambertian" (about the normal, back into the side the ray came from).
+    region:       None, or ((xmin, xmax), (ymin, ymax), (zmin, zmax)) in the node's local frame (None / +-inf entries
+                  are unbounded): the facet covers only the points strictly inside -- a PARTIAL coating such as the
+                  quarter mirror of examples/006 Coatings.ipynb cell 3.
+
+    Where a facet states a reflectivity below 1 but no refracted ray exists (total internal reflection, transmit
+    "refract"), the ray reflects: a coating does not repeal Snell's law.
     """
 
-    def __init__(self, normal, reflectivity=None, transmit="refract", reflect="specular", atol=1e-6):
+    def __init__(self, normal, reflectivity=None, transmit="refract", reflect="specular", atol=1e-6, region=None):
         if transmit not in ("refract", "straight") or reflect not in ("specular", "lambertian"):
             raise ValueError("transmit must be refract|straight and reflect specular|lambertian")
-        if reflectivity is not None and not 0.0 <= float(reflectivity) <= 1.0:
-            raise ValueError("reflectivity must be in [0, 1]")
         self.normal = tuple(float(v) for v in normal)
-        self.reflectivity = None if reflectivity is None else float(reflectivity)
+        self.reflectivity = None
+        self.spectrum = None  # (x, R) arrays of a tabulated reflectivity
+        if reflectivity is not None and np.ndim(reflectivity) == 0:
+            if not 0.0 <= float(reflectivity) <= 1.0:
+                raise ValueError("reflectivity must be in [0, 1]")
+            self.reflectivity = float(reflectivity)
+        elif reflectivity is not None:
+            table = np.asarray(reflectivity, dtype=float)
+            if table.ndim != 2 or table.shape[1] != 2 or len(table) < 1 or (np.diff(table[:, 0]) < 0).any():
+                raise ValueError("a reflectivity spectrum is an (n, 2) array of (wavelength, reflectivity), wavelengths ascending")
+            if (table[:, 1] < 0.0).any() or (table[:, 1] > 1.0).any():
+                raise ValueError("reflectivity must be in [0, 1]")
+            self.spectrum = (table[:, 0].copy(), table[:, 1].copy())
         self.transmit = transmit
         self.reflect = reflect
         self.atol = float(atol)
+        lo, hi = [-np.inf] * 3, [np.inf] * 3
+        if region is not None:
+            if len(region) != 3:
+                raise ValueError("region is ((xmin, xmax), (ymin, ymax), (zmin, zmax))")
+            for k, bounds in enumerate(region):
+                if bounds is None:
+                    continue
+                lo[k] = -np.inf if bounds[0] is None else float(bounds[0])
+                hi[k] = np.inf if bounds[1] is None else float(bounds[1])
+        self.region = (tuple(lo), tuple(hi))
 
-    def matches(self, normal) -> bool:
-        return all(abs(a - b) <= self.atol for a, b in zip(self.normal, normal))
+    def matches(self, normal, position=None) -> bool:
+        if not all(abs(a - b) <= self.atol for a, b in zip(self.normal, normal)):
+            return False
+        if position is None:
+            return True
+        lo, hi = self.region
+        return all(l < float(p) < h for l, p, h in zip(lo, position, hi))
+
+    def reflectivity_at(self, wavelength):
+        """The stated reflectivity at `wavelength`, None when the facet keeps Fresnel."""
+        if self.spectrum is not None:
+            return float(np.clip(np.interp(wavelength, self.spectrum[0], self.spectrum[1]), 0.0, 1.0))
+        return self.reflectivity
 
 
 class FacetSurfaceDelegate(FresnelSurfaceDelegate):
@@ -103,15 +142,44 @@ class FacetSurfaceDelegate(FresnelSurfaceDelegate):
     def _facet(self, ray, geometry):
         normal = geometry.normal(ray.position)
         for facet in self.facets:
-            if facet.matches(normal):
+            if facet.matches(normal, ray.position):
                 return facet
         return None
 
+    @staticmethod
+    def _no_refracted_ray(ray, geometry, container, adjacent):
+        n1 = container.geometry.material.refractive_index
+        n2 = adjacent.geometry.material.refractive_index
+        if not n2 < n1:
+            return False
+        c = float(np.clip(_incident_normal(ray, geometry) @ np.asarray(ray.direction, dtype=float), -1.0, 1.0))
+        return np.sqrt(max(1.0 - c * c, 0.0)) * (n1 / n2) > 1.0
+
     def reflectivity(self, surface, ray, geometry, container, adjacent):
         facet = self._facet(ray, geometry)
-        if facet is not None and facet.reflectivity is not None:
-            return facet.reflectivity
+        stated = None if facet is None else facet.reflectivity_at(ray.wavelength)
+        if stated is not None:
+            if facet.transmit == "refract" and self._no_refracted_ray(ray, geometry, container, adjacent):
+                return 1.0
+            return stated
         return super(FacetSurfaceDelegate, self).reflectivity(surface, ray, geometry, container, adjacent)
+
+    def reflected_direction(self, surface, ray, geometry, container, adjacent):
+        facet = self._facet(ray, geometry)
+        if facet is not None and facet.reflect == "lambertian":
+            from pvtrace_b200.material.utils import lambertian
+
+            back = -_incident_normal(ray, geometry)  # the hemisphere the ray arrived from
+            x, y, z = lambertian()  # about +z (material/utils.py:173-186)
+            if back[2] < -0.9999999:
+                t1, t2 = np.array((0.0, -1.0, 0.0)), np.array((-1.0, 0.0, 0.0))
+            else:
+                a = 1.0 / (1.0 + back[2])
+                b = -back[0] * back[1] * a
+                t1 = np.array((1.0 - back[0] * back[0] * a, b, -back[0]))
+                t2 = np.array((b, 1.0 - back[1] * back[1] * a, -back[1]))
+            return tuple((x * t1 + y * t2 + z * back).tolist())
+        return super(FacetSurfaceDelegate, self).reflected_direction(surface, ray, geometry, container, adjacent)
 
     def transmitted_direction(self, surface, ray, geometry, container, adjacent):
         facet = self._facet(ray, geometry)

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_struct_layout():
     lib = _cuda.load_library()
-    assert lib.pvt_version() == 100
+    assert lib.pvt_version() == 200
     # the ctypes mirrors must have the compiled structs' sizes (load_library() enforces it as well)
     sizes = (ctypes.c_int32 * 4)()
     lib.pvt_struct_sizes(sizes)
