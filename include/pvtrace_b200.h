@@ -219,6 +219,10 @@ const char* pvt_last_error(void);
  * binding verify its struct mirrors against the compiled library */
 void        pvt_struct_sizes(int32_t sizes[4]);
 
+/* Measured fp64 FMA throughput of the device in TFLOP/s (2 flops per FMA): eight independent chains per thread on every
+ * scheduler.  bench.py reports the tracer's fp64 rate against it (the bound that governs it is issue latency, not HBM). */
+int         pvt_measure_fp64_peak(int device, double* tflops);
+
 /* ---------------------------------------------------------------- drop-in trace (host buffers) -------- *
  * Replaces _kernel.trace_bundle (_kernel.pyx:903-1115).  `positions`/`directions` are [n,3], `wavelengths`
  * [n] host arrays and are not modified (the reference copies them, :1064-1065).  When `emit` is non-NULL the

@@ -676,19 +676,27 @@ static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, c
     // arrays front to back in chunks (plain copies of the columns that are not constant) followed, in stream order, by
     // the new mark = rays complete so far.  CTAs claim photons in index order, so they consume the prefix as it lands.
     // Upload and trace overlap completely: total time ~ max(PCIe, kernel) + the trace of the LAST chunk -- hence chunks
-    // that start small (the kernel gets going at once), double up to a fifth of what is left (few, efficient copies)
-    // and shrink again towards the end (little left to trace when the last byte lands).
+    // that start small (the kernel gets going at once), grow up to a fifth of what is left (few, efficient copies) and
+    // shrink again towards the end (little left to trace when the last byte lands).  They grow by a quarter, not by
+    // doubling: the kernel traces chunk k while chunk k + 1 lands, so a chunk must not take longer to upload than its
+    // predecessor takes to trace.  With the constant columns gone the upload is only ~1.3x faster than the trace
+    // (240 MB in 4.8 ms against 6.2 ms), and doubling chunks left the kernel waiting at every step of the ramp
+    // (measured: trace done at 6.9 ms instead of 6.3).
     streamed = true;
     if (n >= kElideMinRays && elision_allowed()) scan.start(positions, directions, wavelengths, n, scan_threads());
     const RayConstants& consts = scan.found;
     rc = path.rays.reserve(7 * n);
     double *d_pos = path.rays.ptr, *d_dir = path.rays.ptr + 3 * n, *d_wl = path.rays.ptr + 6 * n;
-    size_t min_chunk = kStreamChunkRays, shrink_div = 5;
+    size_t min_chunk = kStreamChunkRays, shrink_div = 5, growth_pct = 125;
+    if (const char* env = getenv("PVT_UPLOAD_GROWTH_PCT")) { const int v = atoi(env); if (v >= 100 && v <= 400) growth_pct = (size_t)v; }
     if (const char* env = getenv("PVT_UPLOAD_MIN_CHUNK")) { const long v = atol(env); if (v >= 1024) min_chunk = (size_t)v; }
     if (const char* env = getenv("PVT_UPLOAD_SHRINK")) { const int v = atoi(env); if (v >= 2 && v <= 64) shrink_div = (size_t)v; }
     int chunks = 0;
     cudaError_t e = cudaSuccess;
     uint32_t* h_marks = path.h_marks;
+    const bool dbg_on = getenv("PVT_DEBUG_TIMING") != nullptr;  // how long the copy stream took, when the trace ended
+    cudaEvent_t dbg[2] = {nullptr, nullptr};
+    if (dbg_on) { cudaEventCreate(&dbg[0]); cudaEventCreate(&dbg[1]); cudaEventRecord(dbg[0], s_copy); }
     if (!rc) e = cudaMemsetAsync(c->arrived.ptr, 0, 4, s_copy);
     if (!rc && e == cudaSuccess) e = cudaEventRecord(path.uploaded[0], s_copy);
     if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(s_run, path.uploaded[0], 0);
@@ -702,7 +710,7 @@ static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, c
         const size_t left = n - lo;
         size_t m = left / shrink_div > min_chunk ? left / shrink_div : min_chunk;
         if (m > grow) m = grow;
-        grow *= 2;
+        grow = grow * growth_pct / 100;
         if (m > left || chunks == kMaxChunks - 1 || left - m < min_chunk / 2) m = left;
         if (!(consts.mask & 1u)) {
           e = cudaMemcpyAsync(d_pos + 3 * lo, positions + 3 * lo, 24 * m, cudaMemcpyHostToDevice, s_copy);
@@ -722,8 +730,23 @@ static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, c
         ++chunks;
       }
     }
-    if (getenv("PVT_DEBUG_TIMING")) fprintf(stderr, "[pvt] device %d: constant columns mask %u, %d upload chunks, %lld bytes\n",
-                                            params->device, consts.mask, chunks, h2d_bytes);
+    if (dbg_on) {
+      cudaEventRecord(dbg[1], s_copy);
+      cudaEventSynchronize(dbg[1]);
+      const bool ok = scan.finish();
+      cudaEvent_t done;
+      cudaEventCreate(&done);
+      cudaEventRecord(done, s_run);
+      cudaEventSynchronize(done);
+      float up = 0.f, t_start = 0.f, total = 0.f;
+      cudaEventElapsedTime(&up, dbg[0], dbg[1]);
+      cudaEventElapsedTime(&t_start, t0, dbg[0]);
+      cudaEventElapsedTime(&total, t0, done);
+      fprintf(stderr, "[pvt] device %d: constant columns mask %u (%s), %d upload chunks, %lld bytes; upload started %.3f ms after "
+              "t0 and took %.3f ms; trace done at %.3f ms\n", params->device, consts.mask, ok ? "confirmed" : "REFUTED", chunks,
+              h2d_bytes, t_start, up, total);
+      cudaEventDestroy(dbg[0]); cudaEventDestroy(dbg[1]); cudaEventDestroy(done);
+    }
     if (!rc && e != cudaSuccess) {
       // never leave the kernel polling: publish "everything arrived" so it drains, then report
       h_marks[kMaxChunks - 1] = 0xffffffffu;
@@ -965,6 +988,31 @@ extern "C" int pvt_intersect_bundle(const pvt_scene_t* scene, const double* posi
 
 // ---------------------------------------------------------------------------------------------------------
 // Library queries
+
+extern "C" int pvt_measure_fp64_peak(int device, double* tflops) {
+  if (!tflops) return fail("tflops is NULL");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail("no CUDA device is usable (pvtrace_b200 has no CPU fallback)");
+  PVT_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PVT_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int grid = prop.multiProcessorCount * 8, iterations = 1 << 14;
+  DeviceBuffer<double> out;
+  PVT_TRY(out.reserve((size_t)grid * 256));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {  // (the first warms up)
+    Timer timer;
+    PVT_TRY(timer.start());
+    fp64_peak_kernel<<<grid, 256>>>(out.ptr, iterations);
+    PVT_CUDA(cudaGetLastError());
+    double seconds = 0.0;
+    PVT_TRY(timer.stop(&seconds));
+    const double rate = 2.0 * 8.0 * iterations * (double)grid * 256.0 / seconds * 1e-12;
+    if (rep > 0 && rate > best) best = rate;
+  }
+  *tflops = best;
+  return 0;
+}
 
 extern "C" int pvt_version(void) { return PVT_VERSION; }
 extern "C" int pvt_device_count(void) {

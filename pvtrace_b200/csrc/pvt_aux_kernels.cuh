@@ -19,6 +19,24 @@ __global__ void __launch_bounds__(256) emit_kernel(const double* blob, double* p
   }
 }
 
+// fp64 FMA throughput of the chip, measured: eight independent chains per thread, every scheduler saturated.  The
+// denominator of the tracer's COMPUTE roofline ("measure a DFMA microbenchmark before quoting a compute
+// fraction"); 2 flops per FMA.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iterations) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-3 * (threadIdx.x + 32 * k);
+  const double b = 0.999999, c = 1e-7;
+  for (int i = 0; i < iterations; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+  }
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += a[k];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
 // tallies <-> packed doubles (the buffer a multi-GPU caller all-reduces)
 __global__ void pack_tallies_kernel(const u64* ints_a, int n_a, const double* sums, int n_s, const u64* bins, int n_b,
                                     double* packed) {
