@@ -548,8 +548,8 @@ constexpr size_t kScanBlockRows = 1 << 14;
 class ConstantScan {
  public:
   RayConstants found;
-  // decides the candidates from the first rows and starts checking the rest on `threads - 1` workers
-  void start(const double* pos, const double* dir, const double* wl, size_t n, int threads) {
+  // decides the candidates from the first rows (cheap: the upload can be planned at once) ...
+  void probe(const double* pos, const double* dir, const double* wl, size_t n) {
     cols_[0] = Column{pos, 3}; cols_[1] = Column{dir, 3}; cols_[2] = Column{wl, 1};
     n_ = n;
     const size_t probe = n < kProbeRows ? n : kProbeRows;
@@ -562,6 +562,10 @@ class ConstantScan {
     blocks_per_col_ = (n + kScanBlockRows - 1) / kScanBlockRows;
     next_.store(0);
     failed_.store(false);
+  }
+  // ... and checks the rest of the candidate columns on `threads - 1` workers (started once the copies are enqueued:
+  // creating threads takes as long as uploading a million rays)
+  void start(int threads) {
     if (!found.mask) return;
     for (int t = 1; t < threads; ++t) workers_.emplace_back([this] { work(); });
   }
@@ -683,7 +687,7 @@ static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, c
     // (240 MB in 4.8 ms against 6.2 ms), and doubling chunks left the kernel waiting at every step of the ramp
     // (measured: trace done at 6.9 ms instead of 6.3).
     streamed = true;
-    if (n >= kElideMinRays && elision_allowed()) scan.start(positions, directions, wavelengths, n, scan_threads());
+    if (n >= kElideMinRays && elision_allowed()) scan.probe(positions, directions, wavelengths, n);
     const RayConstants& consts = scan.found;
     rc = path.rays.reserve(7 * n);
     double *d_pos = path.rays.ptr, *d_dir = path.rays.ptr + 3 * n, *d_wl = path.rays.ptr + 6 * n;
@@ -730,6 +734,7 @@ static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, c
         ++chunks;
       }
     }
+    scan.start(scan_threads());
     if (dbg_on) {
       cudaEventRecord(dbg[1], s_copy);
       cudaEventSynchronize(dbg[1]);

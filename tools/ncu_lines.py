@@ -7,8 +7,13 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(root, "pvtrace_b200/csrc/libpvtrace_b200.so")
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=d, stdout=subprocess.DEVNULL)
-cub = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-txt = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout
+# (one cubin per translation unit of the library: take the one that holds the kernel)
+txt = ""
+for cub in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):
+    out = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(d, cub)], stdout=subprocess.PIPE, text=True).stdout
+    if sub in out:
+        txt = out
+        break
 fn = None; cur = None; line_of = {}
 for line in txt.splitlines():
     m = re.match(r'\s*\.text\.(\S+):', line)
