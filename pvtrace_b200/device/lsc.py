@@ -42,6 +42,7 @@ class LSC(object):
         self._air_gap_mirror_info = {"want_air_gap_mirror": False, "lambertian": False}
         self._scene = None
         self._result = None
+        self._store = None  # end-ray rows of every simulate() call so far (the reference appends too)
         self._user_lights = []
         self._user_components = []
 
@@ -160,19 +161,31 @@ class LSC(object):
 
     # -- run + summary -----------------------------------------------------------------------------
 
-    def simulate(self, n, progress=None, emit_method="kT", seed=None, record_every=0, **engine_kwargs):
-        """Trace `n` rays on the GPU; returns the EngineResult (also kept for `counts()`)."""
+    def simulate(self, n, progress=None, emit_method="kT", seed=None, record_every=None, **engine_kwargs):
+        """Trace `n` rays on the GPU; returns the EngineResult.
+
+        Like the reference's (lsc.py:338-377) the call keeps what `report()` / `spectrum()` / `counts()` need -- the
+        entrance and exit rows of the logged rays -- and a second call APPENDS to that store.  The reference logs every
+        ray; here `record_every` defaults to every ray up to 10^5 rays and to a sample of about 10^5 histories beyond
+        (a full log of 10^7 rays would be 150 GB); the recorder tallies (`recorder_counts()`) always cover every ray."""
         from pvtrace_b200 import engine
 
         if self._scene is None:
             self._make_scene()
+        if record_every is None:
+            record_every = max(1, int(n) // 100_000)
         self._result = engine.simulate(self._scene, n, seed=seed, emit_method=emit_method,
                                        record_every=record_every, **engine_kwargs)
+        if self._result.num_recorded:
+            rows = self._rows_of(self._result)
+            self._store = rows if self._store is None else {k: np.concatenate([self._store[k], rows[k]]) for k in rows}
+        if progress:
+            progress(int(n))
         return self._result
 
-    def counts(self):
-        """Distinct-ray counts per LSC face and loss channel: {'escaping': {face: n}, 'reflected': {...},
-        'entering': {...}, 'lost': n, 'exit': n, 'killed': n, 'thrown': n}."""
+    def recorder_counts(self):
+        """Distinct-ray counts of the LAST run's recorders, over every ray (not only the logged ones):
+        {'escaping': {face: n}, 'reflected': {...}, 'entering': {...}, 'lost': n, 'exit': n, 'killed': n, 'thrown': n}."""
         if self._result is None:
             raise ValueError("Run a simulation before calling this method.")
         rec = self._result.recorders
@@ -180,6 +193,11 @@ class LSC(object):
         out.update(lost=rec["lost"].rays, exit=rec["exit"].rays, killed=rec["killed"].rays,
                    thrown=self._result.num_rays)
         return out
+
+    def counts(self):
+        """The reference's surface-count table (lsc.py:455-506): {'Solar In' | 'Solar Out' | 'Luminescent Out' |
+        'Luminescent In': {facet: count}} over the stored end rays of every `simulate` call so far."""
+        return self.counts_table()
 
     # -- report (lsc.py:379-607 rebuilt on the engine's event log instead of per-ray pandas rows) ----------------
 
@@ -194,13 +212,16 @@ class LSC(object):
         event is NONRADIATIVE or REACT count as lost (the reference only tests for ABSORB, which is never last any
         more), and facets are named by their outward normal as the solar-cell delegate names them (lsc.py:38-47:
         near = -y, far = +y; `label_facets`, lsc.py:447-452, has the two swapped)."""
+        if self._result is None:
+            raise ValueError("Run a simulation before calling this method.")
+        if self._store is None:
+            raise ValueError("The report is built from logged histories: simulate(..., record_every=k) with k >= 1.")
+        return self._store
+
+    def _rows_of(self, result):
+        """The end-ray rows of one run (see `_end_rays`); `source` holds the NAME of the light or component."""
         from pvtrace_b200.light.event import Event
 
-        result = self._result
-        if result is None:
-            raise ValueError("Run a simulation before calling this method.")
-        if result.num_recorded == 0:
-            raise ValueError("The report is built from logged histories: simulate(..., record_every=k) with k >= 1.")
         d, m = result.data, result.max_events
         counts = np.asarray(d["counts"], dtype=np.int64)
         base = np.arange(len(counts), dtype=np.int64) * m
@@ -219,23 +240,34 @@ class LSC(object):
             on = np.isclose(position[:, axis], normal[axis] * half[axis], atol=2.220446049250313e-13)
             facet[on] = name
         names = {e.value: e.name.lower() for e in Event}
+        ray_of_row = rows // m  # ordinal of the logged ray each row belongs to
+        recorded = result.recorded_indices
+        components = list(result.compiled.component_names)
+        src = d["source"][rows]
+        source = np.array([components[int(c)] if c >= 0 else result.sources[int(recorded[int(j)])]
+                           for c, j in zip(src, ray_of_row)], dtype=object)
         return {"kind": kinds, "event": np.array([names[int(k)] for k in d["kind"][rows]]), "facet": facet,
-                "luminescent": d["source"][rows] >= 0, "wavelength": d["wavelength"][rows]}
+                "luminescent": src >= 0, "source": source, "wavelength": d["wavelength"][rows]}
 
     def spectrum(self, facets=(), kind="last", source="all", events=None):
-        """Wavelengths of the stored end rays (lsc.py:508-575): kind 'first' (entrance) | 'last' (exit) | None,
-        source 'all' | 'light' | 'luminescent', facets a collection of face names (empty: any), events a collection of
-        lower-case event names (None: any)."""
+        """Wavelengths of the stored end rays (lsc.py:508-575): kind 'first' (entrance) | 'last' (exit) | None;
+        source 'all', the name of a light or component, or a collection of names -- as in the reference -- and, as
+        shorthands, 'light' (any light) | 'luminescent' (any component); facets a collection of face names (empty:
+        any); events a collection of lower-case event names (None: any)."""
         if kind not in (None, "first", "last"):
             raise ValueError("Direction must be either `'first'` or `'last'.`")
-        if source not in ("all", "light", "luminescent"):
-            raise ValueError("Unknown source requested.", source)
         rows = self._end_rays()
         keep = np.ones(len(rows["kind"]), dtype=bool)
         if kind is not None:
             keep &= rows["kind"] == ("entrance" if kind == "first" else "exit")
-        if source != "all":
+        if isinstance(source, str) and source in ("light", "luminescent") and source not in self.light_names() | self.component_names():
             keep &= rows["luminescent"] == (source == "luminescent")
+        elif not (isinstance(source, str) and source == "all"):
+            wanted = {source} if isinstance(source, str) else set(source)
+            unknown = wanted - (self.component_names() | self.light_names())
+            if unknown:
+                raise ValueError("Unknown source requested.", unknown)
+            keep &= np.isin(rows["source"].astype(str), sorted(wanted))
         if len(facets) > 0:
             keep &= np.isin(rows["facet"].astype(str), list(facets))
         if events is not None:

@@ -26,6 +26,7 @@ def traced_lsc(n=1500, seed=7, cells=("left", "right", "near", "far"), mirror=Tr
     data = pvt_oracle.trace_bundle(compiled, None, None, None, seed, 1000, m, EMIT_METHODS["kT"], os.cpu_count() or 1, 1,
                                    emitter=emitter, n=n)
     lsc._result = EngineResult(compiled, data, LightNames(emitter.light_names, n, 0), m, 1, 0.0)
+    lsc._store = lsc._rows_of(lsc._result)  # what LSC.simulate keeps after a run
     return lsc
 
 
@@ -88,6 +89,14 @@ def test_spectrum_filters(capsys):
     first, last = lsc.spectrum(kind="first"), lsc.spectrum(kind="last")
     assert len(everything) == len(first) + len(last) and len(first) == 800
     assert (lsc.spectrum(kind="first", source="light") == 555.0).all()
+    # the reference's form: names of lights / components, alone or as a collection (lsc.py:520-531)
+    assert len(lsc.spectrum(kind="first", source="Light")) == 800
+    by_name = lsc.spectrum(kind="last", source={"Lumogen F Red 305"})
+    assert len(by_name) == len(lsc.spectrum(kind="last", source="luminescent")) > 50
+    assert len(lsc.spectrum(kind="last", source=["Light", "Lumogen F Red 305"])) == len(last)
+    with pytest.raises(ValueError):
+        lsc.spectrum(source="Unobtainium")
+    assert lsc.counts() == lsc.counts_table()
     red = lsc.spectrum(kind="last", source="luminescent", facets={"left", "right", "near", "far"})
     assert len(red) > 50 and red.min() > 555.0  # kT emission: collected light is red-shifted
     by_event = {e: len(lsc.spectrum(kind="last", events={e})) for e in ("nonradiative", "transmit", "reflect", "kill")}
@@ -100,7 +109,7 @@ def test_spectrum_filters(capsys):
 
 def test_report_needs_logged_histories():
     lsc = traced_lsc(n=50)
-    lsc._result.data["counts"] = lsc._result.data["counts"][:0]
+    lsc._store = None  # a run with record_every=0 keeps nothing
     with pytest.raises(ValueError):
         lsc.counts_table()
     with pytest.raises(ValueError):
