@@ -349,12 +349,18 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counters, int word, in
 constexpr int kDrainPhotons = PVT_DRAIN_PHOTONS;  // a CTA with no supply left and at most this many live photons drains them lane by lane
 constexpr int kReqWords = 8;
 // Registers after the re-division (the pool is per CTA: the two sides must add up to what the launch allocated):
-//   S = 128: launched as 640 x 96, becomes 512 x 104 + 128 x 64.
+//   S = 128: launched as 640 x 96, becomes 512 x 112 + 128 x 32.  The tracing warps set the pace and every register they
+//   lack is a spill on their critical path; the service warps have slack (they sleep on their barrier a tenth of the
+//   time) and absorb theirs: 104 + 64 -> 112 + 32 measured -8 % on the trace kernel (6.69 -> 6.16 ms on one lease).
 // setmaxnreg is a WARPGROUP instruction (four warps execute it together): a service side of two warps (S = 64, launched
 // as 576 x 112) cannot re-divide -- it hangs -- and keeps the uniform 112.
 __host__ __device__ constexpr bool redivide_regs(int S) { return S > 0 && S % 128 == 0; }
-__host__ __device__ constexpr int tracer_regs(int S) { return 104; }
-__host__ __device__ constexpr int service_regs(int S) { return 64; }
+#ifndef PVT_TRACER_REGS
+#define PVT_TRACER_REGS 112
+#define PVT_SERVICE_REGS 32
+#endif
+__host__ __device__ constexpr int tracer_regs(int S) { return PVT_TRACER_REGS; }
+__host__ __device__ constexpr int service_regs(int S) { return PVT_SERVICE_REGS; }
 
 template <int T, int S>
 __device__ __forceinline__ void sync_tracers() {
