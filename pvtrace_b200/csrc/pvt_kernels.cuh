@@ -349,18 +349,17 @@ __device__ __forceinline__ uint32_t steal_chunk(uint32_t* counters, int word, in
 constexpr int kDrainPhotons = PVT_DRAIN_PHOTONS;  // a CTA with no supply left and at most this many live photons drains them lane by lane
 constexpr int kReqWords = 8;
 // Registers after the re-division (the pool is per CTA: the two sides must add up to what the launch allocated):
-//   S = 128: launched as 640 x 96, becomes 512 x 112 + 128 x 32.  The tracing warps set the pace and every register they
-//   lack is a spill on their critical path; the service warps have slack (they sleep on their barrier a tenth of the
-//   time) and absorb theirs: 104 + 64 -> 112 + 32 measured -8 % on the trace kernel (6.69 -> 6.16 ms on one lease).
+//   S = 128: launched as 640 x 96, becomes 512 x 112 + 128 x 32 for scenes of axis-aligned boxes (every LSC), 512 x 104 +
+//   128 x 64 otherwise.  The tracing warps set the pace and every register they lack is a spill on their critical path;
+//   in the LSC scenes the service warps have slack (0.25 tally requests per photon step: they sleep on their barrier a
+//   tenth of the time) and absorb the spills instead: 104 + 64 -> 112 + 32 measured -6 to -8 % (config 2: 6.69 -> 6.16 ms,
+//   validation 17.5 -> 16.4 ms, within one lease).  Where nearly every step tallies (hello_world: one request per photon
+//   step) the service side is the busier one and the same move costs 15 % (4.84 -> 5.56 ms).
 // setmaxnreg is a WARPGROUP instruction (four warps execute it together): a service side of two warps (S = 64, launched
 // as 576 x 112) cannot re-divide -- it hangs -- and keeps the uniform 112.
 __host__ __device__ constexpr bool redivide_regs(int S) { return S > 0 && S % 128 == 0; }
-#ifndef PVT_TRACER_REGS
-#define PVT_TRACER_REGS 112
-#define PVT_SERVICE_REGS 32
-#endif
-__host__ __device__ constexpr int tracer_regs(int S) { return PVT_TRACER_REGS; }
-__host__ __device__ constexpr int service_regs(int S) { return PVT_SERVICE_REGS; }
+__host__ __device__ constexpr int tracer_regs(bool boxes) { return boxes ? 112 : 104; }
+__host__ __device__ constexpr int service_regs(bool boxes) { return boxes ? 32 : 64; }
 
 template <int T, int S>
 __device__ __forceinline__ void sync_tracers() {
@@ -495,11 +494,11 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   const bool service = S > 0 && tid >= T;
   const bool svc_rays = S > 0;  // the service warps also fill the ring of fresh rays
   if (service) {
-    if (redivide_regs(S)) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(service_regs(S)));
+    if (redivide_regs(S)) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(service_regs(kBoxes)));
     service_loop<P, K, kSvcWarps>(a, sv, sink, pool, ring, lane);
     __threadfence();
   } else {  // the tracing warps; both roles meet again at retire_cta's barrier below
-  if (redivide_regs(S)) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tracer_regs(S)));
+  if (redivide_regs(S)) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(tracer_regs(kBoxes)));
   uint32_t idle_iterations = 0;
   bool draining = false;
 #ifdef PVT_PROFILE_STAGES  // where warp 0's time goes: stage 1, its barrier, stage 2, its barrier (cycles) -> stats[4..7]
