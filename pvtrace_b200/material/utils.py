@@ -1,9 +1,10 @@
 """Optics and sampling helpers (host float64 versions).
 
 Fresnel / Snell / mirror formulas: pvtrace/material/utils.py:8-45.  Phase functions and surface scattering
-distributions: pvtrace/material/utils.py:104-186.  The device versions live in pvtrace_b200/csrc/pvt_optics.cuh;
-tests/test_optics.py checks the two (and the oracle) against each other and against the reference's
-known answers (tests/test_frensel_reflection.py, tests/test_frensel_refraction.py).
+distributions: pvtrace/material/utils.py:104-186.  The device versions live in pvtrace_b200/csrc/pvt_math.cuh;
+tests/test_gpu_helpers.py checks device, oracle and host against each other, against vectors generated from the
+reference's functions (tests/golden/optics.npz) and against the reference's known answers
+(/root/reference/tests/test_frensel_reflection.py, test_frensel_refraction.py).
 """
 import math
 

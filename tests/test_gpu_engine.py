@@ -91,7 +91,9 @@ def test_histories_look_like_python_histories(gpu):
 
 def test_host_ray_arrays_and_xoshiro_stream_match_reference_semantics(gpu):
     """Host arrays through the drop-in call; with the reference's xoshiro stream the device reproduces the golden
-    event logs of the compiled reference kernel ray for ray (>= 99 % identical sequences, rest within rounding)."""
+    event logs of the compiled reference kernel ray for ray.  The stream is SEQUENTIAL: one comparison that falls the
+    other way by a last-bit difference (device FMA contraction, log / sincos a few ulp from glibc's) re-times every later
+    draw of that ray, so such a ray differs from there on.  96 golden rays per scene: at most one may."""
     for name, method in (("lsc", "kT"), ("mixed", "redshift"), ("fresnel", "kT")):
         g = np.load(os.path.join(GOLDEN, f"engine_{name}_{method}.npz"))
         compiled = pv.engine.compile_scene(scenes.SCENES[name]())
@@ -100,7 +102,7 @@ def test_host_ray_arrays_and_xoshiro_stream_match_reference_semantics(gpu):
                                  EMIT_METHODS[method], 0, 1, rng_mode=_cuda.RNG_XOSHIRO)
         n = len(g["wavelengths"])
         same = (out["counts"] == g["out_counts"]) & (out["kind"].reshape(n, m) == g["out_kind"].reshape(n, m)).all(axis=1)
-        assert same.mean() >= 0.97, (name, same.mean())
+        assert (~same).sum() <= 1, (name, int((~same).sum()), "of", n)
         rows = np.repeat(same, m)
         np.testing.assert_allclose(out["position"][rows], g["out_position"][rows], atol=1e-7)
         np.testing.assert_allclose(out["wavelength"][rows], g["out_wavelength"][rows], atol=1e-7)

@@ -1,5 +1,5 @@
 import time, numpy as np, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import pvtrace_b200 as pv
 from pvtrace_b200.device import configs
 from pvtrace_b200.engine import _cuda
