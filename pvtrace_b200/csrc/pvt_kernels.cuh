@@ -396,7 +396,10 @@ __device__ __forceinline__ void produce_ray(const TraceArgs& a, const SceneView&
   const long long i = sequence_photon(pool.counters, o);
   double* r = pool.ring + (o & (K - 1));
   if (a.has_rays()) {
-    // one ray per lane (measured faster than word-granular cooperative loads of the chunk's 224 doubles);
+    // one ray per lane.  Word-granular cooperative loads of the chunk's columns (lane l takes words l, l + 32, l + 64 of the
+    // contiguous run and scatters them into the ring: every sector fetched once instead of three times) were measured
+    // twice and lost twice -- round 1, and round 2 in the service warps: +2 % on config 2, +13 % on hello_world, where
+    // the service side is the busy one.  The L2 sectors re-touched cost nothing; the index arithmetic does.
     // L2-only loads: with a streaming upload a cached line could hold a neighbour that had not arrived
     if (a.const_mask & 1u) { r[0] = a.cpos[0]; r[K] = a.cpos[1]; r[2 * K] = a.cpos[2]; }
     else { r[0] = __ldcg(a.pos + 3 * i); r[K] = __ldcg(a.pos + 3 * i + 1); r[2 * K] = __ldcg(a.pos + 3 * i + 2); }
