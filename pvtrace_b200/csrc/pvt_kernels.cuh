@@ -150,11 +150,13 @@ __host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 115
 // Shared memory left over is L1: the kernel is sensitive to it (24 KB more of shared memory cost 5 %), so the pool
 // carries nothing it does not need.
 __host__ __device__ constexpr size_t pool_bytes(int P) {
-  return (size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/ + 1 /*tallied*/) +
-         (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/ + 128 /*decoy words of atoms_add_by*/;
+  return ((size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/ + 1 /*tallied*/) +
+          (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/ + 128 /*decoy words of atoms_add_by*/ + 127) / 128 * 128;
 }
+// the pool follows the blob on a 128-byte line, whatever the size of the scene
+__host__ __device__ inline size_t pool_offset(int blob_words) { return (16 + (size_t)blob_words * 8 + 127) / 128 * 128; }
 __host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
-  return 16 + (size_t)blob_words * 8 + pool_bytes(P);
+  return pool_offset(blob_words) + pool_bytes(P);
 }
 
 // counters (u32): [0..1], [4..5] queue lengths (VOLUME | SURFACE << 16, EXIT), double buffered by iteration parity; then
@@ -472,11 +474,13 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   constexpr int K = ring_size(P);
   constexpr int kSvcWarps = S / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // [mbarrier 16 B][blob][pool, on the next 128-byte line].  (The other order -- pool first, so that its columns and
+  // the blob sit at compile-time addresses -- was measured: ptxas spills more with the immediates, +13 %.)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   double* sblob = reinterpret_cast<double*>(smem_raw + 16);
   stage_blob(sblob, a.blob, (uint32_t)a.blob_words * 8u, bar);
   const SceneView sv{sblob, &a.hdr};
-  const PoolView pool = carve_pool(smem_raw + 16 + (size_t)a.blob_words * 8, P);
+  const PoolView pool = carve_pool(smem_raw + pool_offset(a.blob_words), P);
   const int R = sv.hdr().n_recorders;
   const TallySink sink = cta_sink(a, R);
   const u64 id0 = (u64)a.first_index;  // photon index of ray 0 of the bundle within the run
