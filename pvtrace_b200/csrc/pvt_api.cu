@@ -617,9 +617,15 @@ class ConstantScan {
 
 int scan_threads() {
   if (const char* env = getenv("PVT_SCAN_THREADS")) { const int v = atoi(env); if (v >= 1 && v <= 64) return v; }
-  const unsigned hw = std::thread::hardware_concurrency();
+  // half the cores, at most 8 (four already keep up with one GPU's upload); ranks that share the host (torchrun sets
+  // LOCAL_WORLD_SIZE) share its cores
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char* env = getenv("LOCAL_WORLD_SIZE")) {
+    const int ranks = atoi(env);
+    if (ranks > 1) hw = 2 * hw / (unsigned)ranks;
+  }
   const unsigned want = hw / 2 < 8 ? hw / 2 : 8;
-  return want < 1 ? 1 : (int)want;
+  return want < 2 ? 2 : (int)want;
 }
 bool elision_allowed() {
   if (const char* env = getenv("PVT_ELIDE_CONSTANT")) return atoi(env) != 0;
