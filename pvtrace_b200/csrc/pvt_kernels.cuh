@@ -931,6 +931,11 @@ __device__ __forceinline__ uint32_t pack_ids(const Nearest& nh) {
   return (lo & 0xffffu) | (((uint32_t)nh.adjacent & 0xffu) << 16);
 }
 
+#ifndef PVT_INTERSECT_LEAN
+#define PVT_INTERSECT_LEAN 1
+#endif
+constexpr bool kIntersectLean = PVT_INTERSECT_LEAN != 0;  // see nearest_surface_boxes<kLean>
+
 template <bool kPacked>
 __device__ __forceinline__ void store_hit(const Nearest& nh, long long i, double* t0, uint32_t* packed, int32_t* hit,
                                           int32_t* container, int32_t* adjacent) {
@@ -994,7 +999,7 @@ __global__ void __launch_bounds__(THREADS, kMinCtas)
         issue(next, s);
       }
     }
-    const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
+    const Nearest nh = kBoxes ? nearest_surface_boxes<kIntersectLean>(sv, p, d) : nearest_surface(sv, p, d);
     store_hit<kPacked>(nh, tile * THREADS + tid, t0, packed, hit, container, adjacent);
     if (++s == STAGES) { s = 0; parity ^= 1u; }
   }
@@ -1004,7 +1009,7 @@ __global__ void __launch_bounds__(THREADS, kMinCtas)
     if (i < n) {
       const V3 p = V3{__ldcs(pos + 3 * i), __ldcs(pos + 3 * i + 1), __ldcs(pos + 3 * i + 2)};
       const V3 d = V3{__ldcs(dir + 3 * i), __ldcs(dir + 3 * i + 1), __ldcs(dir + 3 * i + 2)};
-      const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
+      const Nearest nh = kBoxes ? nearest_surface_boxes<kIntersectLean>(sv, p, d) : nearest_surface(sv, p, d);
       store_hit<kPacked>(nh, i, t0, packed, hit, container, adjacent);
     }
   }
@@ -1022,7 +1027,7 @@ __global__ void __launch_bounds__(256) intersect_plain_kernel(const __grid_const
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const V3 p = V3{__ldcs(pos + 3 * i), __ldcs(pos + 3 * i + 1), __ldcs(pos + 3 * i + 2)};
     const V3 d = V3{__ldcs(dir + 3 * i), __ldcs(dir + 3 * i + 1), __ldcs(dir + 3 * i + 2)};
-    const Nearest nh = kBoxes ? nearest_surface_boxes(sv, p, d) : nearest_surface(sv, p, d);
+    const Nearest nh = kBoxes ? nearest_surface_boxes<kIntersectLean>(sv, p, d) : nearest_surface(sv, p, d);
     store_hit<kPacked>(nh, i, t0, packed, hit, container, adjacent);
   }
 }

@@ -183,10 +183,12 @@ static __device__ __noinline__ Nearest nearest_surface_boxes_any(const SceneView
   }
   return best.result();
 }
+// kLean: the instruction-lean forms of the parallel test and the reciprocal (pvt_math.cuh), for the intersect stage
+template <bool kLean = false>
 __device__ __forceinline__ Nearest nearest_surface_boxes(const SceneView& sv, const V3& p, const V3& d) {
-  if (slab_parallel(d)) return nearest_surface_boxes_any(sv, p, d);  // (the direction is the same in every node's frame)
+  if (kLean ? slab_parallel_lean(d) : slab_parallel(d)) return nearest_surface_boxes_any(sv, p, d);  // (the direction is the same in every node's frame)
   const int n_nodes = sv.hdr().n_nodes;
-  const V3 inv = slab_reciprocal(d);
+  const V3 inv = kLean ? slab_reciprocal_lean(d) : slab_reciprocal(d);
   const double* rec = sv.node(0);
   TwoNearest best;
   {  // node 0 straight into the empty reduction: what add_pair would select against +inf sentinels

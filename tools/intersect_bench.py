@@ -26,15 +26,19 @@ peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspa
 flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")  # 256 MB > L2
 for label, fn, bytes_per_ray in (("packed", runp, 60), ("3 arrays", run3, 68)):
     for _ in range(3): fn()
-    times = []
-    for _ in range(10):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        times.append(a.elapsed_time(b))
-    ms = sum(times) / len(times)
-    print(f"{name} n={n} variant={os.environ.get('PVT_INTERSECT_VARIANT', '0')} {label}: {ms:.4f} ms (min {min(times):.4f})  "
-          f"{bytes_per_ray * n / ms / 1e6:.0f} GB/s  frac {bytes_per_ray * n / ms / 1e6 / peak:.3f}", flush=True)
+    # "dirty": 256 MB written before the kernel (its dirty lines are written back while the kernel runs);
+    # "clean": written, then read back -- a cold L2 with nothing to write back, like ncu's cache control
+    for kind in ("clean", "dirty"):
+        times = []
+        for _ in range(10):
+            flush.zero_()
+            if kind == "clean": flush.sum()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        ms = sum(times) / len(times)
+        print(f"{name} n={n} variant={os.environ.get('PVT_INTERSECT_VARIANT', '0')} {label} [{kind} L2]: {ms:.4f} ms (min {min(times):.4f})  "
+              f"{bytes_per_ray * n / ms / 1e6:.0f} GB/s  frac {bytes_per_ray * n / ms / 1e6 / peak:.3f}", flush=True)
 p = packed.to(torch.int64) & 0xffffffff
 unpack = lambda sh: torch.where(((p >> sh) & 0xff) == 0xff, torch.full_like(p, -1), (p >> sh) & 0xff).to(torch.int32)
 ok = bool((unpack(0) == ids[0]).all() and (unpack(8) == ids[1]).all() and (unpack(16) == ids[2]).all() and (t0 == t0p).all())
