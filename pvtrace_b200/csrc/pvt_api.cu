@@ -160,7 +160,7 @@ extern "C" int pvt_context_create(const pvt_scene_t* scene, const pvt_emit_t* em
     for (int k = 0; k < wave_variant_count() && want_t >= 0; ++k) {
       const int t = wave_variant(k).threads, pl = wave_variant(k).pool, b = wave_variant(k).ctas;
       if ((want_t && t != want_t) || (want_p && pl != want_p) || (want_b && b != want_b)) continue;
-      size_t need = wavefront_smem_bytes(c->blob_words, pl);
+      size_t need = wavefront_smem_bytes(c->blob_words, pl, t);
       if (const char* env = getenv("PVT_EXTRA_SMEM")) need += (size_t)atoi(env);  // experiment: shrink L1
       if ((need + 1024) * b <= (size_t)prop.sharedMemPerMultiprocessor && need <= (size_t)prop.sharedMemPerBlockOptin) {
         c->wave_threads = t; c->wave_pool = pl; c->wave_ctas = b; c->wave_smem = need;

@@ -106,7 +106,7 @@ __device__ __forceinline__ TallySink cta_sink(const TraceArgs& a, int R) {
 
 // adds the CTA's slab into the context accumulators and the lanes' statistics into g_stats
 __device__ __forceinline__ void retire_cta(const TraceArgs& a, int R, const LaneStats& st) {
-  u64 s_steps = st.steps, s_events = st.events, s_rays = st.rays;
+  u64 s_steps = st.steps, s_events = st.events, s_rays = st.rays;  // (zero for threads that counted in shared memory)
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     s_steps += __shfl_down_sync(kFullMask, s_steps, off);
@@ -149,14 +149,16 @@ constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, i
 __host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 1152) ? 512 : 256; }
 // Shared memory left over is L1: the kernel is sensitive to it (24 KB more of shared memory cost 5 %), so the pool
 // carries nothing it does not need.
-__host__ __device__ constexpr size_t pool_bytes(int P) {
+constexpr int kStatWordsPerThread = 3;  // steps, events, rays of every tracing thread (SmemStats)
+__host__ __device__ constexpr size_t pool_bytes(int P, int T) {
   return ((size_t)P * (kPoolDoubles * 8 + 8 /*seen*/ + kPoolWords * 4 + 3 * 2 /*queues*/ + 1 /*tallied*/) +
-          (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/ + 128 /*decoy words of atoms_add_by*/ + 127) / 128 * 128;
+          (size_t)ring_size(P) * 7 * 8 + 128 /*counters*/ + 128 /*decoy words of atoms_add_by*/ +
+          (size_t)kStatWordsPerThread * 4 * T + 127) / 128 * 128;
 }
 // the pool follows the blob on a 128-byte line, whatever the size of the scene
 __host__ __device__ inline size_t pool_offset(int blob_words) { return (16 + (size_t)blob_words * 8 + 127) / 128 * 128; }
-__host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P) {
-  return pool_offset(blob_words) + pool_bytes(P);
+__host__ __device__ inline size_t wavefront_smem_bytes(int blob_words, int P, int T) {
+  return pool_offset(blob_words) + pool_bytes(P, T);
 }
 
 // counters (u32): [0..1], [4..5] queue lengths (VOLUME | SURFACE << 16, EXIT), double buffered by iteration parity; then
@@ -193,6 +195,7 @@ struct PoolView {
   uint8_t* tallied;    // service-warp kernels: this photon has sent a tally request before (its seen mask is live)
   double* ring;        // [7][K]: px py pz dx dy dz wl of entries [.., ring_hi) of the CTA's ray sequence, at entry mod K
   uint32_t* counters;
+  uint32_t* stats;     // [3][T] steps, events, rays per tracing thread (SmemStats), behind the counters and decoys
 };
 
 __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
@@ -210,10 +213,19 @@ __device__ __forceinline__ PoolView carve_pool(unsigned char* base, int P) {
   v.qv = h; v.qs = h + P; v.qe = h + 2 * P;
   v.tallied = reinterpret_cast<uint8_t*>(h + 3 * P);
   v.counters = reinterpret_cast<uint32_t*>(v.tallied + P);  // P is a multiple of 32: 4-byte aligned
+  v.stats = v.counters + 64;
   return v;
 }
 
-typedef PhotonT<2> PoolPhoton;
+// A pool photon's path length and time of flight stay in their pool columns (MemAcc): -2 % on config 2, -1.2 % on
+// the validation scene against loading them into registers for the length of the interaction.
+typedef PhotonT<2, MemAcc> PoolPhoton;
+constexpr bool kAccInPool = true;
+// binds the accumulators of a pool photon to its slot (before anything reads or writes them)
+__device__ __forceinline__ void bind_slot(const PoolView& pool, int s, PhotonT<2, MemAcc>& ph) {
+  ph.travelled.at = pool.trav + s; ph.duration.at = pool.dur + s;
+}
+__device__ __forceinline__ void bind_slot(const PoolView&, int, PhotonT<2>&) {}
 
 // what classify needs of a slot
 template <bool kLog>
@@ -223,8 +235,10 @@ __device__ __forceinline__ void load_slot_head(const PoolView& pool, int s, Pool
   ph.wl = pool.wl[s];
   ph.count = pool.count[s];
   ph.log_ray = -1; ph.log_base = -1; ph.nlog = 0;
+  bind_slot(pool, s, ph);
   if (kLog) {
-    ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; ph.source = pool.source[s];
+    if (!kAccInPool) { ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; }
+    ph.source = pool.source[s];
     ph.nlog = pool.nlog[s];
     ph.log_ray = pool.log_ray[s];
     ph.log_base = ph.log_ray < 0 ? -1 : (long long)ph.log_ray * max_events;
@@ -233,7 +247,8 @@ __device__ __forceinline__ void load_slot_head(const PoolView& pool, int s, Pool
 template <bool kLog, bool kSeen = true>
 __device__ __forceinline__ void load_slot(const PoolView& pool, int s, PoolPhoton& ph, int max_events) {
   load_slot_head<kLog>(pool, s, ph, max_events);
-  ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; ph.source = pool.source[s];
+  if (!kAccInPool) { ph.travelled = pool.trav[s]; ph.duration = pool.dur[s]; }
+  ph.source = pool.source[s];
   const u64 seen = kSeen ? pool.seen[s] : 0ull;  // (the service warps own the masks when there are any)
   ph.seen[0] = (uint32_t)seen; ph.seen[1] = (uint32_t)(seen >> 32);
 }
@@ -241,7 +256,8 @@ template <bool kLog>
 __device__ __forceinline__ void store_slot(const PoolView& pool, int s, const PoolPhoton& ph) {
   pool.px[s] = ph.p.x; pool.py[s] = ph.p.y; pool.pz[s] = ph.p.z;
   pool.dx[s] = ph.d.x; pool.dy[s] = ph.d.y; pool.dz[s] = ph.d.z;
-  pool.wl[s] = ph.wl; pool.trav[s] = ph.travelled; pool.dur[s] = ph.duration;
+  pool.wl[s] = ph.wl;
+  if (!kAccInPool) { pool.trav[s] = ph.travelled; pool.dur[s] = ph.duration; }
   pool.source[s] = ph.source;
   if (kLog) pool.nlog[s] = ph.nlog;
 }
@@ -362,6 +378,11 @@ constexpr int kReqWords = 8;
 __host__ __device__ constexpr bool redivide_regs(int S) { return S > 0 && S % 128 == 0; }
 __host__ __device__ constexpr int tracer_regs(bool boxes) { return boxes ? 112 : 104; }
 __host__ __device__ constexpr int service_regs(bool boxes) { return boxes ? 32 : 64; }
+
+#ifndef PVT_BOX_SURFACE
+#define PVT_BOX_SURFACE 1
+#endif
+constexpr bool kBoxSurface = PVT_BOX_SURFACE != 0;  // surface_step / exit_step specialised for axis-aligned boxes
 
 template <int T, int S>
 __device__ __forceinline__ void sync_tracers() {
@@ -490,13 +511,15 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < kCtrCount) pool.counters[tid] = tid == kSvcAck ? (uint32_t)kSvcWarps : 0u;
   for (int s = tid; s < P; s += T + S) pool.count[s] = -1;
+  for (int k = tid; k < kStatWordsPerThread * T; k += T + S) pool.stats[k] = 0u;
   __syncthreads();
   if (tid == 0) {  // the first blocks of this CTA's sequence: enough to fill the pool
     for (int k = 0; k < (P + (int)kClaim - 1) / (int)kClaim && k < 3; ++k) extend_sequence(a, pool.counters, (uint32_t)P);
   }
   __syncthreads();
 
-  LaneStats st;
+  // run statistics in shared memory, not in registers (see SmemStats; with early_u: -1.2 % config 2, -4.5 % validation)
+  SmemStats<T> st{smem_addr(pool.stats + (tid < T ? tid : 0))};
   double* const ring = S > 0 ? a.requests + (size_t)blockIdx.x * 2 * kReqWords * P : nullptr;  // two halves, by parity
   const bool service = S > 0 && tid >= T;
   const bool svc_rays = S > 0;  // the service warps also fill the ring of fresh rays
@@ -603,6 +626,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         if (chunk < classify_chunks) {
           const int slot = (int)(chunk * 32u) + lane;
           PoolPhoton ph;
+          bind_slot(pool, slot, ph);
           const bool dead = pool.count[slot] < 0;
           const unsigned m = __ballot_sync(kFullMask, dead);
           bool fresh = false;
@@ -644,14 +668,14 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
             PhiloxStream rng;
             rng.init(a.keys, id0 + (u64)pool.idx[slot]);
             StepPlan plan;
-            cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan);
+            cls = classify_step<kLog, kBoxes>(sv, L, sp, ph, rng, st, plan, pool.u + slot);  // (stores the step's pool.u itself)
             if (cls == kDead) {
               if (kLog && ph.log_ray >= 0) L.counts[ph.log_ray] = ph.nlog;
               pool.count[slot] = -1;
             } else {
               if (fresh) store_slot<kLog>(pool, slot, ph);
               pool.count[slot] = ph.count;
-              pool.t[slot] = plan.t; pool.u[slot] = plan.u; pool.alpha[slot] = plan.alpha;
+              pool.t[slot] = plan.t; pool.alpha[slot] = plan.alpha;
               pool.ids[slot] = (uint32_t)(plan.hit & 0xff) | ((uint32_t)(plan.container & 0xff) << 8) |
                                ((uint32_t)(plan.adjacent & 0xff) << 16) | (cls == kKill ? 1u << 24 : 0u);
               live = true;
@@ -713,9 +737,9 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         plan.hit = (int)(ids & 0xff); plan.container = (int)((ids >> 8) & 0xff); plan.adjacent = (int)((ids >> 16) & 0xff);
         if (plan.adjacent == 0xff) plan.adjacent = -1;
         if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
-        else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
+        else if (cls == kSurface) alive = surface_step<kLog, kBoxes && kBoxSurface>(sv, L, sp, ph, rng, st, plan, tr);
         else if (ids >> 24) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
-        else exit_step<kLog>(sv, L, sp, ph, st, plan, tr);
+        else exit_step<kLog, kBoxes && kBoxSurface>(sv, L, sp, ph, st, plan, tr);
         if (alive) {
           store_slot<kLog>(pool, slot, ph);
         } else {
@@ -766,8 +790,8 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         bool alive = false;
         TallyReq tr;
         if (cls == kVolume) alive = volume_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
-        else if (cls == kSurface) alive = surface_step<kLog>(sv, L, sp, ph, rng, st, plan, tr);
-        else if (cls == kExit) exit_step<kLog>(sv, L, sp, ph, st, plan, tr);
+        else if (cls == kSurface) alive = surface_step<kLog, kBoxes && kBoxSurface>(sv, L, sp, ph, rng, st, plan, tr);
+        else if (cls == kExit) exit_step<kLog, kBoxes && kBoxSurface>(sv, L, sp, ph, st, plan, tr);
         else if (cls == kKill) kill_step<kLog>(sv, L, sp, ph, st, plan, tr);
         if (tr.sel >= 0) tally(sv, sink, ph, tr);
         if (!alive) break;
@@ -802,7 +826,9 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
 #endif
 #endif
   }  // tracing warps
-  retire_cta(a, R, st);
+  LaneStats mine;  // a thread's own three words: written by nobody else
+  if (tid < T) { mine.steps = pool.stats[tid]; mine.events = pool.stats[T + tid]; mine.rays = pool.stats[2 * T + tid]; }
+  retire_cta(a, R, mine);
 }
 
 // =========================================================================================================

@@ -43,10 +43,21 @@ struct StepParams {
 };
 
 // Photon state carried between steps.  `seen` is the distinct-ray mask of up to 32 * kSeenWords recorders.
-template <int kSeenWords>
+// An accumulator that lives in (shared) memory: read, assigned and added to in place.  The wavefront kernel keeps a
+// photon's path length and time of flight in their pool columns this way instead of in four registers that are live
+// through the whole interaction just to be stored back at its end.
+struct MemAcc {
+  double* at;
+  __device__ __forceinline__ operator double() const { return *at; }
+  __device__ __forceinline__ MemAcc& operator=(double v) { *at = v; return *this; }
+  __device__ __forceinline__ MemAcc& operator+=(double v) { *at += v; return *this; }
+};
+
+template <int kSeenWords, class Acc = double>
 struct PhotonT {
   V3 p, d;
-  double wl, travelled, duration;
+  double wl;
+  Acc travelled, duration;
   int32_t source, count, nlog;
   int32_t log_ray;     // ordinal of this ray among the recorded ones (index into counts), < 0: not sampled
   long long log_base;  // first log row of this ray == log_ray * max_events, < 0 when the ray is not sampled
@@ -184,11 +195,14 @@ static __device__ __noinline__ Nearest nearest_surface_boxes_any(const SceneView
   return best.result();
 }
 // kLean: the instruction-lean forms of the parallel test and the reciprocal (pvt_math.cuh), for the intersect stage
-template <bool kLean = false>
+#ifndef PVT_TRACE_LEAN_RCP
+#define PVT_TRACE_LEAN_RCP 1  // the Newton reciprocal in the trace kernels too: -1.3 to -2 % on the LSC configs (one lease)
+#endif
+template <bool kLean = false, bool kLeanRcp = kLean || PVT_TRACE_LEAN_RCP != 0>
 __device__ __forceinline__ Nearest nearest_surface_boxes(const SceneView& sv, const V3& p, const V3& d) {
   if (kLean ? slab_parallel_lean(d) : slab_parallel(d)) return nearest_surface_boxes_any(sv, p, d);  // (the direction is the same in every node's frame)
   const int n_nodes = sv.hdr().n_nodes;
-  const V3 inv = kLean ? slab_reciprocal_lean(d) : slab_reciprocal(d);
+  const V3 inv = kLeanRcp ? slab_reciprocal_lean(d) : slab_reciprocal(d);
   const double* rec = sv.node(0);
   TwoNearest best;
   {  // node 0 straight into the empty reduction: what add_pair would select against +inf sentinels
@@ -398,15 +412,30 @@ __device__ __forceinline__ void advance(P& ph, double t, double slowness) {
 // Per-lane run statistics (device counters of pvt_out_t.stats)
 struct LaneStats {
   uint32_t steps = 0, events = 0, rays = 0;
+  __device__ __forceinline__ void step() { ++steps; }
+  __device__ __forceinline__ void event() { ++events; }
+  __device__ __forceinline__ void ray() { ++rays; }
+};
+// The same counters as three words of the thread's own in SHARED memory, bumped by reductions that return nothing
+// (RED.shared: one instruction, no register, nothing to wait for).  Counters that live for the whole kernel and change
+// two or three times per photon step are the first thing a register allocator under pressure spills: as registers they
+// were local-memory round trips in the wavefront kernel.  T = stride between the three arrays.
+template <int T>
+struct SmemStats {
+  uint32_t at;  // shared-memory address of this thread's step counter
+  __device__ __forceinline__ static void bump(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+  __device__ __forceinline__ void step() { bump(at); }
+  __device__ __forceinline__ void event() { bump(at + 4u * T); }
+  __device__ __forceinline__ void ray() { bump(at + 8u * T); }
 };
 
-template <bool kLog, class P>
-__device__ __forceinline__ void begin_photon(P& ph, const LogColumns& L, const StepParams& sp, LaneStats& st) {
+template <bool kLog, class P, class St>
+__device__ __forceinline__ void begin_photon(P& ph, const LogColumns& L, const StepParams& sp, St& st) {
   ph.travelled = 0.0; ph.duration = 0.0;
   ph.source = -1; ph.count = 0; ph.nlog = 0;
 #pragma unroll
   for (int w = 0; w < (int)(sizeof(ph.seen) / 4); ++w) ph.seen[w] = 0u;
-  ++st.rays; ++st.events;
+  st.ray(); st.event();
   PVT_LOG(ph, PVT_EV_GENERATE, -1, -1, -1, -1);
 }
 
@@ -420,25 +449,28 @@ struct StepPlan {
 
 // First half of the reference's loop body (_kernel.pyx:654-760): budget check, intersect, kill check, free path.
 // Touches nothing but position, direction, wavelength and the step counter.
-template <bool kLog, bool kBoxes = false, class Rng, class P>
+// `u_slot`: where an addressed stream's surface uniform goes as soon as it is drawn -- the pool column of the wavefront
+// kernel -- instead of staying live across the intersection just to be stored afterwards (plan.u is then not set).
+template <bool kLog, bool kBoxes = false, class Rng, class P, class St>
 __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
-                                                   Rng& rng, LaneStats& st, StepPlan& plan) {
+                                                   Rng& rng, St& st, StepPlan& plan, double* u_slot = nullptr) {
   const Header& H = sv.hdr();
   plan.u = 1.0; plan.alpha = 0.0;
   ++ph.count;
   rng.begin_step((uint32_t)ph.count);
   // event budget of sampled rays: keep room for the KILL record (:658-663)
   if (kLog && ph.log_base >= 0 && ph.nlog >= sp.max_events - 1) {
-    ++st.events;
+    st.event();
     PVT_LOG(ph, PVT_EV_KILL, -1, -1, -1, -1);
     return kDead;
   }
-  ++st.steps;
+  st.step();
   // Addressed streams draw the step's two uniforms (free path, surface test) BEFORE the intersection: the ten Philox
   // rounds and the logarithm are chains that depend on nothing else, and issued here they overlap the slab arithmetic
   // instead of following it (the kernel is bound by dependent-issue latency, not by issue slots: -3 % on config 2).
   double ud_early = 0.0, u_early = 1.0;
   if (Rng::kAddressed) rng.pair(kBlockPath, ud_early, u_early);
+  if (Rng::kAddressed && u_slot != nullptr) { *u_slot = u_early; u_early = 1.0; }
   const Nearest nh = kBoxes ? nearest_surface_boxes(sv, ph.p, ph.d) : nearest_surface(sv, ph.p, ph.d);
   if (nh.total == 0) return kDead;  // :681-682
   plan.hit = nh.hit; plan.container = nh.container; plan.adjacent = nh.adjacent;
@@ -447,6 +479,9 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
   if (nh.hit == H.root_id) return kExit;
 
   // Beer-Lambert free path in the container (material.py:17-47 == :746-760)
+  // (Computing the coefficient and the free path AHEAD of the intersection -- possible where one node alone has
+  // components, as in every LSC: they depend on the wavelength and the draw only -- shortens the dependent chain and
+  // was measured 8 % SLOWER: two more doubles live across the slab tests, spilled.  Registers bound this kernel.)
   const int c0 = sv.node_int(nh.container, NI_COMP_START), cn = sv.node_int(nh.container, NI_COMP_COUNT);
   double alpha = 0.0;
   for (int k = 0; k < cn; ++k) alpha += absorption_at(sv, c0 + k, ph.wl);
@@ -458,7 +493,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
     } else {
       ud = rng.one(kBlockPath, 0);
     }
-    const double depth = -log(1.0 - ud) / alpha;
+    const double depth = PVT_DIV(-log(1.0 - ud), alpha);
     if (depth < nh.t0) {
       plan.t = depth;
       return kVolume;
@@ -470,10 +505,10 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
 }
 
 // Step budget exhausted (:716-723): KILL record and `killed` tally on the container, no movement.
-template <bool kLog, class P>
+template <bool kLog, class P, class St>
 __device__ __forceinline__ void kill_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
-                                          LaneStats& st, const StepPlan& plan, TallyReq& tr) {
-  ++st.events;
+                                          St& st, const StepPlan& plan, TallyReq& tr) {
+  st.event();
   PVT_LOG(ph, PVT_EV_KILL, -1, plan.container, -1, -1);
   if (sv.hdr().n_recorders > 0 && sv.has_recorders(plan.container, PVT_REC_KILLED)) {
     tr.sel = PVT_REC_KILLED; tr.node = plan.container; tr.has_normal = false; tr.normal = V3{0.0, 0.0, 0.0};
@@ -482,29 +517,41 @@ __device__ __forceinline__ void kill_step(const SceneView& sv, const LogColumns&
 }
 
 // Leaves the scene through the root boundary (:728-744).
-template <bool kLog, class P>
+// kBoxes (scenes of axis-aligned boxes only, as in nearest_surface_boxes): the local point is a translation away, the
+// normal is +-e_ax in both frames and every product with it is a component pick -- the values the general expressions
+// give (multiplications by exact zeros and ones), without forming them.
+template <bool kLog, bool kBoxes = false, class P, class St>
 __device__ __forceinline__ void exit_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
-                                          LaneStats& st, const StepPlan& plan, TallyReq& tr) {
+                                          St& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit;
   advance(ph, plan.t, sv.node(plan.container)[kNodeSlowness]);
-  ++st.events;
+  st.event();
   PVT_LOG(ph, PVT_EV_EXIT, hit, plan.container, plan.adjacent, -1);
   if (sv.hdr().n_recorders > 0 && sv.has_recorders(hit, PVT_REC_EXIT)) {
     const double* rec = sv.node(hit);
-    const V3 lp = map_point(rec + kNodeW2L, ph.p);
+    V3 lp, nw;
     int face;
-    const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), rec + kNodeParams, lp, face);
-    const V3 nw = map_vector(rec + kNodeL2W, nl);
-    double c = fabs(dot(nw, ph.d));
+    double c;
+    if (kBoxes) {
+      lp = V3{ph.p.x + rec[kNodeW2L + 3], ph.p.y + rec[kNodeW2L + 7], ph.p.z + rec[kNodeW2L + 11]};
+      face = box_face(rec + kNodeParams, lp);
+      nw = axis_vector(face >> 1, (face & 1) ? 1.0 : -1.0);
+      c = fabs(component(ph.d, face >> 1));
+    } else {
+      lp = map_point(rec + kNodeW2L, ph.p);
+      const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), rec + kNodeParams, lp, face);
+      nw = map_vector(rec + kNodeL2W, nl);
+      c = fabs(dot(nw, ph.d));
+    }
     if (c > 1.0) c = 1.0;
     tr.sel = PVT_REC_EXIT; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c;
   }
 }
 
 // Absorbed in the volume (:762-832).  Returns true while the photon lives (re-emitted or scattered).
-template <bool kLog, class Rng, class P>
+template <bool kLog, class Rng, class P, class St>
 __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
-                                            Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
+                                            Rng& rng, St& st, const StepPlan& plan, TallyReq& tr) {
   const Header& H = sv.hdr();
   const int container = plan.container;
   advance(ph, plan.t, sv.node(container)[kNodeSlowness]);
@@ -526,7 +573,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
     running += absorption_at(sv, c0 + k, ph.wl);
     if (target <= running) { comp = c0 + k; break; }
   }
-  ++st.events;
+  st.event();
   PVT_LOG(ph, PVT_EV_ABSORB, -1, container, -1, comp);
   const double* cr = sv.comp(comp);
   const int ctype = sv.comp_int(comp, CI_TYPE);
@@ -541,7 +588,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
     else rng.pair(kBlockPhase, g1, g2);
     ph.d = phase_direction(sv.comp_int(comp, CI_PHASE), cr[kCompPhaseParam], g1, g2);
     ph.source = comp;
-    ++st.events;
+    st.event();
     if (ctype == PVT_COMP_LUMINOPHORE) {  // component.py:381-440 == :795-812
       const int es = sv.comp_int(comp, CI_EMS_START), en = sv.comp_int(comp, CI_EMS_N);
       const double* ex = sv.w + H.off_ems_x + es;
@@ -549,7 +596,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
       double p1 = 0.0;
       if (sp.emit_method != PVT_EMIT_FULL) {
         double nm = ph.wl;
-        if (sp.emit_method == PVT_EMIT_KT) nm = 1240.0 / (1240.0 / nm + 1.5 * kBoltzmannEv * 300.0);
+        if (sp.emit_method == PVT_EMIT_KT) nm = PVT_DIV(1240.0, PVT_DIV(1240.0, nm) + 1.5 * kBoltzmannEv * 300.0);
         p1 = interp_hinted(nm, ex, ec, en, cr[kCompEmsInvDx]);
       }
       double u_gamma, u_delay;
@@ -569,7 +616,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
     return true;
   }
   if (cr[kCompTauNr] > 0.0) ph.duration += -log(1.0 - rng.one_rare(kBlockEmit, 1)) * cr[kCompTauNr];
-  ++st.events;
+  st.event();
   int sel;
   if (ctype == PVT_COMP_REACTOR) {
     PVT_LOG(ph, PVT_EV_REACT, -1, container, -1, comp);
@@ -586,32 +633,44 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
 }
 
 // Reaches a surface that is not the root boundary (:834-895).  Returns true while the photon lives.
-template <bool kLog, class Rng, class P>
+template <bool kLog, bool kBoxes = false, class Rng, class P, class St>
 __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColumns& L, const StepParams& sp, P& ph,
-                                             Rng& rng, LaneStats& st, const StepPlan& plan, TallyReq& tr) {
+                                             Rng& rng, St& st, const StepPlan& plan, TallyReq& tr) {
   const int hit = plan.hit, container = plan.container, adjacent = plan.adjacent;
   const double n1 = sv.node(container)[kNodeIndex];
   advance(ph, plan.t, sv.node(container)[kNodeSlowness]);
-  ++st.events;
+  st.event();
   if (adjacent < 0) {
     PVT_LOG(ph, PVT_EV_KILL, hit, container, -1, -1);
     return false;
   }
   const double* hrec = sv.node(hit);
-  const V3 lp = map_point(hrec + kNodeW2L, ph.p);
-  int face;
-  const V3 nl = outward_normal(sv.node_int(hit, NI_GEOM), hrec + kNodeParams, lp, face);
-  const V3 nw = map_vector(hrec + kNodeL2W, nl);
-  V3 nf = nw;
-  if (dot(nf, ph.d) < 0.0) nf = neg(nf);
-  double c = dot(nf, ph.d);  // cosine of the incidence angle, in [0, 1] up to rounding
+  V3 lp, nl, nw, nf;
+  int face, ax = 0;
+  double c, sg = 1.0, sf = 1.0, d_ax = 0.0;  // kBoxes: nl = nw = sg e_ax, nf = sf e_ax, d_ax = the direction's ax component
+  if (kBoxes) {
+    lp = V3{ph.p.x + hrec[kNodeW2L + 3], ph.p.y + hrec[kNodeW2L + 7], ph.p.z + hrec[kNodeW2L + 11]};
+    face = box_face(hrec + kNodeParams, lp);
+    ax = face >> 1; sg = (face & 1) ? 1.0 : -1.0;
+    d_ax = component(ph.d, ax);
+    sf = sg * d_ax < 0.0 ? -sg : sg;  // the normal turned along the ray
+    c = sf * d_ax;
+  } else {
+    lp = map_point(hrec + kNodeW2L, ph.p);
+    nl = outward_normal(sv.node_int(hit, NI_GEOM), hrec + kNodeParams, lp, face);
+    nw = map_vector(hrec + kNodeL2W, nl);
+    nf = nw;
+    if (dot(nf, ph.d) < 0.0) nf = neg(nf);
+    c = dot(nf, ph.d);  // cosine of the incidence angle, in [0, 1] up to rounding
+  }
+  const double c_raw = c;
   c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
 
   const bool fresnel = sv.node_int(hit, NI_SURF) == PVT_SURF_FRESNEL;
   const double n2 = sv.node(adjacent)[kNodeIndex];
   double R = 0.0;
   bool straight = false, lambert = false, fixed_R = false;
-  const int facet = find_facet(sv, hit, nl, lp);
+  const int facet = sv.hdr().n_facets > 0 ? find_facet(sv, hit, kBoxes ? axis_vector(ax, sg) : nl, lp) : -1;
   if (facet >= 0) {
     const int flags = sv.facet_flags(facet);
     straight = (flags & PVT_FACET_TRANSMIT_STRAIGHT) != 0;
@@ -627,7 +686,7 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
     // a coating does not repeal Snell's law: where no refracted ray exists (total internal reflection) a facet that
     // transmits by refraction reflects, whatever reflectivity it states (the square root in snell() would be of a
     // negative number)
-    if (fixed_R && fresnel && !straight && n2 < n1 && sqrt(fmax(1.0 - c * c, 0.0)) * (n1 / n2) > 1.0) R = 1.0;
+    if (fixed_R && fresnel && !straight && n2 < n1 && sqrt(fmax(1.0 - c * c, 0.0)) * PVT_DIV(n1, n2) > 1.0) R = 1.0;
   }
   if (!fixed_R && fresnel) R = fresnel_R_cos(c, n1, n2);
 
@@ -639,19 +698,31 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
     if (lambert) {
       double p1, p2;
       rng.pair_rare(kBlockLambert, p1, p2);
-      ph.d = lambert_about(neg(nf), p1, p2);
+      ph.d = lambert_about(kBoxes ? axis_vector(ax, -sf) : neg(nf), p1, p2);
+    } else if (kBoxes) {
+      ph.d = with_component(ph.d, ax, -d_ax);  // mirror(): d - 2 (d . n) n with n = +-e_ax
     } else {
       ph.d = mirror(ph.d, nw);
     }
-    PVT_LOG_N(ph, PVT_EV_REFLECT, hit, container, adjacent, -1, true, nw);
+    PVT_LOG_N(ph, PVT_EV_REFLECT, hit, container, adjacent, -1, true, (kBoxes ? axis_vector(ax, sg) : nw));
     sel = PVT_REC_REFLECTED;
     record = record && container != hit;
   } else {
-    if (fresnel && !straight) ph.d = snell(ph.d, nf, n1, n2);
-    PVT_LOG_N(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, true, nw);
+    if (fresnel && !straight) {
+      if (kBoxes) {  // snell(): n d + f nf with nf = sf e_ax and d . nf = c_raw >= 0
+        const double n = PVT_DIV(n1, n2);
+        const double f = sqrt(1.0 - n * n * (1.0 - c_raw * c_raw)) - n * c_raw;
+        ph.d = with_component(V3{n * ph.d.x, n * ph.d.y, n * ph.d.z}, ax, n * d_ax + f * sf);
+      } else {
+        ph.d = snell(ph.d, nf, n1, n2);
+      }
+    }
+    PVT_LOG_N(ph, PVT_EV_TRANSMIT, hit, container, adjacent, -1, true, (kBoxes ? axis_vector(ax, sg) : nw));
     sel = container == hit ? PVT_REC_ESCAPING : PVT_REC_ENTERING;
   }
-  if (record && sv.has_recorders(hit, sel)) { tr.sel = sel; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = nw; tr.lp = lp; tr.cosine = c; }
+  if (record && sv.has_recorders(hit, sel)) {
+    tr.sel = sel; tr.node = hit; tr.face = face; tr.has_normal = true; tr.normal = kBoxes ? axis_vector(ax, sg) : nw; tr.lp = lp; tr.cosine = c;
+  }
   return true;
 }
 
