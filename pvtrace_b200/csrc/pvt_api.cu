@@ -1131,6 +1131,16 @@ extern "C" int pvt_test_interp(int64_t n, const double* x, int32_t m, const doub
   test_interp_kernel<<<blocks(n), 256>>>(n, a, m, b, c, uniform_inv_dx(xs, m), o);
   return finish_test(out, o, n);
 }
+extern "C" int pvt_test_math(int64_t n, int32_t op, const double* a, const double* b, double* out, int device) {
+  PVT_TRY(begin_test(device));
+  if (n <= 0) return 0;
+  if (op < 0 || op > 2) return fail("pvt_test_math: op must be 0 (log), 1 (divide) or 2 (reciprocal)");
+  Scratch s;
+  double *da = s.up(a, n), *db = s.up(b ? b : a, n), *o = s.up<double>(nullptr, n);
+  PVT_NEED(da && db && o);
+  test_math_kernel<<<blocks(n), 256>>>(n, op, da, db, o);
+  return finish_test(out, o, n);
+}
 extern "C" int pvt_test_rng_uniform(int64_t n_rays, int32_t n_draws, uint64_t seed, int64_t first_index, int32_t rng_mode, double* out, int device) {
   PVT_TRY(begin_test(device));
   if (n_rays <= 0 || n_draws <= 0) return 0;

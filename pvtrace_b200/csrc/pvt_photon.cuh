@@ -493,7 +493,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
     } else {
       ud = rng.one(kBlockPath, 0);
     }
-    const double depth = PVT_DIV(-log(1.0 - ud), alpha);
+    const double depth = PVT_DIV(-PVT_LOG1M(ud), alpha);
     if (depth < nh.t0) {
       plan.t = depth;
       return kVolume;
@@ -607,7 +607,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
                                               : interp(gamma, ec, ex, en);
       if (cr[kCompTauRad] > 0.0) {
         if (!Rng::kAddressed) u_delay = rng.one(kBlockEmit, 1);
-        ph.duration += -log(1.0 - u_delay) * cr[kCompTauRad];
+        ph.duration += -PVT_LOG1M(u_delay) * cr[kCompTauRad];
       }
       PVT_LOG(ph, PVT_EV_EMIT, -1, container, -1, comp);
     } else {
@@ -615,7 +615,7 @@ __device__ __forceinline__ bool volume_step(const SceneView& sv, const LogColumn
     }
     return true;
   }
-  if (cr[kCompTauNr] > 0.0) ph.duration += -log(1.0 - rng.one_rare(kBlockEmit, 1)) * cr[kCompTauNr];
+  if (cr[kCompTauNr] > 0.0) ph.duration += -PVT_LOG1M(rng.one_rare(kBlockEmit, 1)) * cr[kCompTauNr];
   st.event();
   int sel;
   if (ctype == PVT_COMP_REACTOR) {

@@ -242,6 +242,7 @@ def load_library():
         "pvt_test_intersect": (C.c_int, [C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int]),
         "pvt_test_local_normal": (C.c_int, [C.c_int64, vp, vp, vp, vp, C.c_int]),
         "pvt_test_interp": (C.c_int, [C.c_int64, vp, C.c_int32, vp, vp, vp, C.c_int]),
+        "pvt_test_math": (C.c_int, [C.c_int64, C.c_int32, vp, vp, vp, C.c_int]),
         "pvt_test_rng_uniform": (C.c_int, [C.c_int64, C.c_int32, C.c_uint64, C.c_int64, C.c_int32, vp, C.c_int]),
         "pvt_test_sample_phase": (C.c_int, [C.c_int64, C.c_int32, C.c_double, C.c_uint64, C.c_int32, vp, C.c_int]),
     }
@@ -263,7 +264,7 @@ EXPORTED_SYMBOLS = (
     "pvt_context_pack_tallies", "pvt_context_unpack_tallies", "pvt_emit_device", "pvt_emit_bundle",
     "pvt_intersect_bundle", "pvt_intersect_device", "pvt_intersect_device_packed", "pvt_test_fresnel_reflectivity",
     "pvt_test_specular_reflect", "pvt_test_fresnel_refract", "pvt_test_intersect", "pvt_test_local_normal",
-    "pvt_test_interp", "pvt_test_rng_uniform", "pvt_test_sample_phase",
+    "pvt_test_interp", "pvt_test_rng_uniform", "pvt_test_sample_phase", "pvt_test_math",
 )
 
 

@@ -168,3 +168,41 @@ def test_phase_functions_match_oracle(gpu):
         want = pvt_oracle.sample_phase(20000, ptype, prm, 5, _cuda.RNG_PHILOX)
         np.testing.assert_allclose(out, want, rtol=0, atol=1e-9)
         np.testing.assert_allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-12)
+
+
+def dev_math(op, a, b=None):
+    a = _f64(a)
+    b = None if b is None else _f64(b)
+    out = np.zeros_like(a)
+    _cuda.check(_cuda.load_library().pvt_test_math(len(a), op, _cuda._vp(a), _cuda._vp(b), _cuda._vp(out), 0), "math")
+    return out
+
+
+def test_lean_log_division_and_reciprocal_against_libm(gpu):
+    """The trace kernels' own log(1 - u), a / b and 1 / x (pvt_math.cuh: no special cases, no slow paths) against
+    numpy's: the logarithm to one ulp (the library log() it replaces promises the same), the division and the
+    reciprocal correctly rounded in all but a 1e-9 sliver of the arguments (and never more than one ulp off)."""
+    rng = np.random.default_rng(11)
+    u = rng.integers(0, 1 << 53, 2_000_000, dtype=np.uint64).astype(np.float64) / float(1 << 53)
+    x = np.concatenate([1.0 - u, np.ldexp(1.0 - u[:200000], -rng.integers(0, 53, 200000)),
+                        [1.0, 0.5, 2.0 ** -53, np.nextafter(1.0, 0.0), np.sqrt(0.5), np.sqrt(2.0) / 2 * (1 + 1e-16)]])
+    x = x[x > 0]
+    got, ref = dev_math(0, x), np.log(x)
+    ulp = np.spacing(np.abs(ref))
+    err = np.abs(got - ref) / np.where(ulp > 0, ulp, 1.0)
+    assert err.max() <= 1.0 + 1e-9, err.max()
+    assert got[x == 1.0].tolist() == [0.0] * int((x == 1.0).sum())
+    assert (got != ref).mean() < 0.15  # mostly the correctly rounded value
+    # a / b over the operand ranges of the path: indices, absorption coefficients, Fresnel terms, knot spacings
+    a = rng.uniform(-1e3, 1e3, 2_000_000) * 10.0 ** rng.integers(-8, 4, 2_000_000)
+    b = rng.uniform(0.5, 2.0, 2_000_000) * 10.0 ** rng.integers(-8, 5, 2_000_000) * rng.choice([-1.0, 1.0], 2_000_000)
+    q, exact = dev_math(1, a, b), a / b
+    off = q != exact
+    assert off.mean() < 1e-6, off.mean()
+    assert np.all(np.abs(q[off] - exact[off]) <= np.spacing(np.abs(exact[off])))
+    d = np.concatenate([rng.uniform(-1.0, 1.0, 2_000_000), 10.0 ** rng.uniform(-300, 0, 200000), [1.0, -1.0, 1e-300]])
+    d = d[np.abs(d) >= 1e-300]
+    r, exact = dev_math(2, d), 1.0 / d
+    off = r != exact
+    assert off.mean() < 1e-6, off.mean()
+    assert np.all(np.abs(r[off] - exact[off]) <= np.spacing(np.abs(exact[off])))
