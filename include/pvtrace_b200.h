@@ -303,7 +303,8 @@ int pvt_test_local_normal(int64_t n, const int32_t* geom_type, const double* par
 /* _kernel.pyx:219-238 (np.interp with edge clamping) over one table xs/ys[m] */
 int pvt_test_interp(int64_t n, const double* x, int32_t m, const double* xs, const double* ys, double* out, int device);
 /* the device's own arithmetic helpers (no reference counterpart: the reference calls libm's log and the C division,
-   _kernel.pyx:746-760): op 0 log(a) for normal positive a, 1 a / b, 2 1 / a, as the trace kernels compute them */
+   _kernel.pyx:746-760): op 0 log(a) for normal positive a, 1 a / b, 2 1 / a, 3 sqrt(a) for a in [0, 1],
+   as the trace kernels compute them */
 int pvt_test_math(int64_t n, int32_t op, const double* a, const double* b, double* out, int device);
 /* draws[n_rays, n_draws] of the per-ray uniform stream (rng_mode, seed + first_index + i) */
 int pvt_test_rng_uniform(int64_t n_rays, int32_t n_draws, uint64_t seed, int64_t first_index, int32_t rng_mode, double* out, int device);

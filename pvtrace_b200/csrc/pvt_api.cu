@@ -1134,7 +1134,7 @@ extern "C" int pvt_test_interp(int64_t n, const double* x, int32_t m, const doub
 extern "C" int pvt_test_math(int64_t n, int32_t op, const double* a, const double* b, double* out, int device) {
   PVT_TRY(begin_test(device));
   if (n <= 0) return 0;
-  if (op < 0 || op > 2) return fail("pvt_test_math: op must be 0 (log), 1 (divide) or 2 (reciprocal)");
+  if (op < 0 || op > 3) return fail("pvt_test_math: op must be 0 (log), 1 (divide), 2 (reciprocal) or 3 (sqrt)");
   Scratch s;
   double *da = s.up(a, n), *db = s.up(b ? b : a, n), *o = s.up<double>(nullptr, n);
   PVT_NEED(da && db && o);

@@ -103,11 +103,13 @@ __global__ void test_interp_kernel(long long n, const double* x, int m, const do
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = interp_hinted(x[i], xs, ys, m, inv_dx);
 }
-// op 0: log_lean(a), 1: div_newton(a, b), 2: rcp_newton(a) -- the lean forms of pvt_math.cuh against libm / IEEE division
+// op 0: log_lean(a), 1: div_newton(a, b), 2: rcp_newton(a), 3: sqrt_lean(a) --
+// the lean forms of pvt_math.cuh against libm / IEEE arithmetic
 __global__ void test_math_kernel(long long n, int op, const double* a, const double* b, double* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = op == 0 ? log_lean(a[i]) : (op == 1 ? div_newton(a[i], b[i]) : rcp_newton(a[i]));
+  if (op <= 2) { out[i] = op == 0 ? log_lean(a[i]) : (op == 1 ? div_newton(a[i], b[i]) : rcp_newton(a[i])); return; }
+  out[i] = sqrt_lean(a[i]);
 }
 template <class Rng>
 __global__ void test_rng_kernel(long long n_rays, int n_draws, u64 seed, long long first_index, double* out) {

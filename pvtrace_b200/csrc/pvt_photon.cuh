@@ -686,7 +686,7 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
     // a coating does not repeal Snell's law: where no refracted ray exists (total internal reflection) a facet that
     // transmits by refraction reflects, whatever reflectivity it states (the square root in snell() would be of a
     // negative number)
-    if (fixed_R && fresnel && !straight && n2 < n1 && sqrt(fmax(1.0 - c * c, 0.0)) * PVT_DIV(n1, n2) > 1.0) R = 1.0;
+    if (fixed_R && fresnel && !straight && n2 < n1 && PVT_SQRT(fmax(1.0 - c * c, 0.0)) * PVT_DIV(n1, n2) > 1.0) R = 1.0;
   }
   if (!fixed_R && fresnel) R = fresnel_R_cos(c, n1, n2);
 
@@ -711,7 +711,7 @@ __device__ __forceinline__ bool surface_step(const SceneView& sv, const LogColum
     if (fresnel && !straight) {
       if (kBoxes) {  // snell(): n d + f nf with nf = sf e_ax and d . nf = c_raw >= 0
         const double n = PVT_DIV(n1, n2);
-        const double f = sqrt(1.0 - n * n * (1.0 - c_raw * c_raw)) - n * c_raw;
+        const double f = PVT_SQRT(1.0 - n * n * (1.0 - c_raw * c_raw)) - n * c_raw;
         ph.d = with_component(V3{n * ph.d.x, n * ph.d.y, n * ph.d.z}, ax, n * d_ax + f * sf);
       } else {
         ph.d = snell(ph.d, nf, n1, n2);

@@ -206,3 +206,6 @@ def test_lean_log_division_and_reciprocal_against_libm(gpu):
     off = r != exact
     assert off.mean() < 1e-6, off.mean()
     assert np.all(np.abs(r[off] - exact[off]) <= np.spacing(np.abs(exact[off])))
+    # square root of [0, 1] arguments (1 - c^2): the IEEE value
+    x = np.concatenate([rng.uniform(0, 1, 2_000_000), 1.0 - rng.uniform(0, 1, 500000) ** 2, [0.0, 1.0, 1e-300, 2.0 ** -52]])
+    np.testing.assert_array_equal(dev_math(3, x), np.sqrt(x))
