@@ -146,7 +146,10 @@ static __device__ __noinline__ int sampled_ordinal(long long i, long long record
 // three u16 queues; then the ring of prefetched initial rays (7 f64 columns of K entries) and the counters.
 constexpr int kPoolDoubles = 12;  // px py pz dx dy dz wl travelled duration | plan of the step: t, u, alpha
 constexpr int kPoolWords = 6;     // count (< 0: slot is empty), source, nlog, idx, ids, log_ray (< 0: not sampled)
-__host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 1152) ? 512 : 256; }
+#ifndef PVT_RING
+#define PVT_RING 512  // (256: +13 % on config 2 -- refills outrun the ring and fetch their rays themselves)
+#endif
+__host__ __device__ constexpr int ring_size(int P) { return (P > 512 && P <= 1152) ? PVT_RING : 256; }
 // Shared memory left over is L1: the kernel is sensitive to it (24 KB more of shared memory cost 5 %), so the pool
 // carries nothing it does not need.
 constexpr int kStatWordsPerThread = 3;  // steps, events, rays of every tracing thread (SmemStats)
