@@ -471,7 +471,7 @@ __device__ __forceinline__ StepClass classify_step(const SceneView& sv, const Lo
   double ud_early = 0.0, u_early = 1.0;
   if (Rng::kAddressed) rng.pair(kBlockPath, ud_early, u_early);
   if (Rng::kAddressed && u_slot != nullptr) { *u_slot = u_early; u_early = 1.0; }
-  const Nearest nh = kBoxes ? nearest_surface_boxes(sv, ph.p, ph.d) : nearest_surface(sv, ph.p, ph.d);
+  const Nearest nh = kBoxes ? nearest_surface_boxes<true>(sv, ph.p, ph.d) : nearest_surface(sv, ph.p, ph.d);
   if (nh.total == 0) return kDead;  // :681-682
   plan.hit = nh.hit; plan.container = nh.container; plan.adjacent = nh.adjacent;
   plan.t = nh.t0;
