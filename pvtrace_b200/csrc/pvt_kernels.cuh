@@ -2,8 +2,8 @@
 //
 //   wavefront_kernel  THE tracer.  Persistent CTAs (one per SM) around a pool of live photons held as a structure of
 //                     arrays in SHARED MEMORY; CTAs claim blocks of photons from a global counter as their pools
-//                     drain.  Every loop iteration of the 16 tracing warps runs two barrier-separated stages, in
-//                     both of which every warp takes chunks of 32 work items from a shared counter:
+//                     drain.  Every loop iteration of the 16 tracing warps runs two barrier-separated stages over
+//                     chunks of 32 work items (stage 1's dealt round-robin, stage 2's taken from a shared counter):
 //                       1. refill + classify: retired slots take the next ray from a shared-memory ring of fresh
 //                          rays; live photons draw the step's uniforms, are intersected with every node and get
 //                          their free path; the slot index is appended to the VOLUME, SURFACE or EXIT queue (warp
@@ -549,8 +549,8 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
   for (uint32_t iter = 0;; ++iter) {
     uint32_t* qn = pool.counters + 4 * (iter & 1);  // queue lengths of this iteration: VOLUME | SURFACE << 16, EXIT
     // ---------------- stage 1: refill + classify the pool, 32 slots per chunk ----------------------------------
-    // Every warp takes chunks from one shared counter until the stage's work list is empty, so no warp has a
-    // fixed share (kernels without service warps also produce the fresh rays here, first).
+    // (Kernels without service warps also produce the fresh rays here, first, and take both kinds of chunk from one
+    // shared counter; with service warps the classification chunks are dealt round-robin, see below.)
     bool live = false;
     if (S > 0 && tid < 32) {
       // Warp 0 hands the service warps their work for this iteration and wakes them: the tally requests written by
