@@ -178,10 +178,11 @@ def dev_math(op, a, b=None):
     return out
 
 
-def test_lean_log_division_and_reciprocal_against_libm(gpu):
-    """The trace kernels' own log(1 - u), a / b and 1 / x (pvt_math.cuh: no special cases, no slow paths) against
+def test_lean_arithmetic_against_libm(gpu):
+    """The trace kernels' own log(1 - u), a / b, 1 / x and sqrt (pvt_math.cuh: no special cases, no slow paths) against
     numpy's: the logarithm to one ulp (the library log() it replaces promises the same), the division and the
-    reciprocal correctly rounded in all but a 1e-9 sliver of the arguments (and never more than one ulp off)."""
+    reciprocal correctly rounded in all but a 1e-9 sliver of the arguments (and never more than one ulp off), the
+    square root of [0, 1] arguments equal to the IEEE one."""
     rng = np.random.default_rng(11)
     u = rng.integers(0, 1 << 53, 2_000_000, dtype=np.uint64).astype(np.float64) / float(1 << 53)
     x = np.concatenate([1.0 - u, np.ldexp(1.0 - u[:200000], -rng.integers(0, 53, 200000)),
