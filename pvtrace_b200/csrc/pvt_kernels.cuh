@@ -639,6 +639,7 @@ __global__ void __launch_bounds__(T + S, B) wavefront_kernel(const __grid_consta
         if (chunk < classify_chunks) {
           const int slot = (int)(chunk * 32u) + lane;
           PoolPhoton ph;
+          // (loading every lane's slot here, ahead of the refill's atomic and outside the branch below: +1 %)
           bind_slot(pool, slot, ph);
           const bool dead = pool.count[slot] < 0;
           const unsigned m = __ballot_sync(kFullMask, dead);
