@@ -469,7 +469,7 @@ struct Timer {
 
 constexpr int kMaxChunks = 64;           // pieces a host bundle is uploaded + traced in
 constexpr size_t kMinChunkRays = 1 << 20;  // ... of at least this many rays each (separate launches)
-constexpr size_t kStreamChunkRays = 1 << 16;  // smallest chunk of the streaming upload (one launch, arrival marks)
+constexpr size_t kStreamChunkRays = 1 << 17;  // smallest chunk of the streaming upload (one launch, arrival marks)
 constexpr int kMaxDevices = 64;
 
 // What the host-buffer entry points keep PER DEVICE: the cached context (bundles of the same scene -- engine.simulate_stream,
@@ -687,17 +687,18 @@ static int trace_host_bundle(const pvt_scene_t* scene, const pvt_emit_t* emit, c
     // the new mark = rays complete so far.  CTAs claim photons in index order, so they consume the prefix as it lands.
     // Upload and trace overlap completely: total time ~ max(PCIe, kernel) + the trace of the LAST chunk -- hence chunks
     // that start small (the kernel gets going at once), grow up to a fifth of what is left (few, efficient copies) and
-    // shrink again towards the end (little left to trace when the last byte lands).  They grow by a quarter, not by
+    // shrink again towards the end (little left to trace when the last byte lands).  They grow by a tenth, not by
     // doubling: the kernel traces chunk k while chunk k + 1 lands, so a chunk must not take longer to upload than its
-    // predecessor takes to trace.  With the constant columns gone the upload is only ~1.3x faster than the trace
-    // (240 MB in 4.8 ms against 6.2 ms), and doubling chunks left the kernel waiting at every step of the ramp
-    // (measured: trace done at 6.9 ms instead of 6.3).
+    // predecessor takes to trace.  With the constant columns gone the upload is only ~1.15x faster than the trace
+    // (240 MB in 4.4 ms against 5.0 ms), and doubling chunks left the kernel waiting at every step of the ramp
+    // (measured with the kernel at 6.2 ms: trace done at 6.9 ms instead of 6.3; with it at 5.0 ms, growth 105 / 110 /
+    // 115 / 125 / 150 % from 64 K rays: 5.65 / 5.60 / 5.58 / 5.62 / 5.70 ms, 110 % from 128 K rays: 5.53 ms).
     streamed = true;
     if (n >= kElideMinRays && elision_allowed()) scan.probe(positions, directions, wavelengths, n);
     const RayConstants& consts = scan.found;
     rc = path.rays.reserve(7 * n);
     double *d_pos = path.rays.ptr, *d_dir = path.rays.ptr + 3 * n, *d_wl = path.rays.ptr + 6 * n;
-    size_t min_chunk = kStreamChunkRays, shrink_div = 5, growth_pct = 125;
+    size_t min_chunk = kStreamChunkRays, shrink_div = 5, growth_pct = 110;
     if (const char* env = getenv("PVT_UPLOAD_GROWTH_PCT")) { const int v = atoi(env); if (v >= 100 && v <= 400) growth_pct = (size_t)v; }
     if (const char* env = getenv("PVT_UPLOAD_MIN_CHUNK")) { const long v = atol(env); if (v >= 1024) min_chunk = (size_t)v; }
     if (const char* env = getenv("PVT_UPLOAD_SHRINK")) { const int v = atoi(env); if (v >= 2 && v <= 64) shrink_div = (size_t)v; }

@@ -1,4 +1,4 @@
-"""Host-ray end to end against the streaming upload's chunk schedule (PVT_UPLOAD_MIN_CHUNK / PVT_UPLOAD_SHRINK)."""
+"""Host-ray end to end against the streaming upload's chunk schedule (PVT_UPLOAD_MIN_CHUNK / _SHRINK / _GROWTH_PCT)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -16,10 +16,17 @@ ctx.emit(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), n, seed=1)
 for a, b in zip(h, d): a.copy_(b)
 torch.cuda.synchronize()
 arrs = [t.numpy() for t in h]
-for mc, sh in ((65536, 5), (131072, 5), (131072, 4), (262144, 4), (262144, 3), (524288, 3), (32768, 6)):
-    os.environ["PVT_UPLOAD_MIN_CHUNK"] = str(mc); os.environ["PVT_UPLOAD_SHRINK"] = str(sh)
-    best = 1e9
-    for rep in range(4):
-        out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
-        best = min(best, el)
-    print(f"min_chunk={mc} shrink=1/{sh}: device-elapsed best {best*1e3:.2f} ms", flush=True)
+grid = [(65536, 5, g) for g in (105, 110, 115, 125, 150)] + [(32768, 5, 110), (131072, 5, 110), (65536, 8, 110), (65536, 4, 110)]
+if len(sys.argv) > 1 and sys.argv[1] == "chunks":
+    grid = [(mc, sh, 125) for mc, sh in ((65536, 5), (131072, 5), (131072, 4), (262144, 4), (262144, 3), (524288, 3), (32768, 6))]
+for pass_ in range(2):  # interleaved: two passes over the grid
+    for mc, sh, g in grid:
+        os.environ["PVT_UPLOAD_MIN_CHUNK"] = str(mc); os.environ["PVT_UPLOAD_SHRINK"] = str(sh)
+        os.environ["PVT_UPLOAD_GROWTH_PCT"] = str(g)
+        times, walls = [], []
+        for rep in range(5):
+            tic = time.perf_counter()
+            out, el = _cuda.trace_bundle(compiled, arrs[0], arrs[1], arrs[2], 1, 1000, 128, 0, 0, 0, return_elapsed=True)
+            walls.append(time.perf_counter() - tic); times.append(el)
+        print(f"min_chunk={mc} shrink=1/{sh} growth={g}%: device-elapsed best {min(times)*1e3:.3f} median {sorted(times)[2]*1e3:.3f} ms, "
+              f"wall median {sorted(walls)[2]*1e3:.3f} ms", flush=True)
