@@ -227,3 +227,50 @@ def test_addressed_philox_draws_give_the_reference_statistics_on_random_scenes(s
         z = np.abs(a[busy] - b[busy]) / np.sqrt(a[busy] + b[busy])
         assert z.max() <= 4.5 and (z > 3.0).mean() < 0.02, (z.max(), (z > 3.0).mean(), int(busy.sum()))
     assert int(got["rec_distinct"].sum()) > n // 2  # the recorders really see the rays
+
+
+# ---- the host API's geometry against the reference's (Scene.intersections / Node.intersections, the sphere
+# and cylinder roots and normals) -- Box goes through trimesh in the reference, absent here, and is pinned through the
+# compiled kernel instead (tests above, tests/test_oracle_pinning.py) -----------------------------------------------
+def round_scene(ns, seed):
+    rng = np.random.default_rng(seed)
+    world = ns.Node(name="world", geometry=ns.Sphere(radius=30.0, material=ns.Material(refractive_index=1.0)))
+    parents = [world]
+    for k in range(int(rng.integers(2, 7))):
+        mat = ns.Material(refractive_index=float(rng.uniform(1.1, 1.9)))
+        geom = ns.Sphere(radius=float(rng.uniform(0.3, 2.0)), material=mat) if rng.random() < 0.5 else \
+            ns.Cylinder(length=float(rng.uniform(0.5, 4.0)), radius=float(rng.uniform(0.2, 1.5)), material=mat)
+        parent = parents[int(rng.integers(0, len(parents)))] if rng.random() < 0.4 else world
+        node = ns.Node(name=f"n{k}", parent=parent, geometry=geom)
+        node.translate(tuple(float(v) for v in rng.uniform(-3.0, 3.0, 3)))
+        if rng.random() < 0.7:
+            axis = rng.normal(size=3)
+            node.rotate(float(rng.uniform(-3.0, 3.0)), tuple(float(v) for v in axis / np.linalg.norm(axis)))
+        parents.append(node)
+    return ns.Scene(world)
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_scene_intersections_equal_the_reference(seed):
+    """Scene.intersections (pvtrace/scene/scene.py:153-195): the same hits, in the same order, at the same points and
+    distances for rays from all over a random scene of nested, rotated spheres and cylinders; and the outward normals of
+    both geometries at the hit points (sphere.py:63-74, cylinder.py:52-65)."""
+    a, b = round_scene(ours(), 500 + seed), round_scene(reference(), 500 + seed)
+    rng = np.random.default_rng(600 + seed)
+    hits = 0
+    for _ in range(120):
+        origin = tuple(float(v) for v in rng.uniform(-5.0, 5.0, 3))
+        d = rng.normal(size=3)
+        direction = tuple(float(v) for v in d / np.linalg.norm(d))
+        got, want = a.intersections(origin, direction), b.intersections(origin, direction)
+        assert [i.hit.name for i in got] == [i.hit.name for i in want]
+        for g, w in zip(got, want):
+            np.testing.assert_allclose(g.point, w.point, rtol=0, atol=1e-9)
+            assert abs(g.distance - w.distance) <= 1e-9
+            assert g.coordsys.name == w.coordsys.name == "world"
+            # outward normal of the hit geometry at the hit point, in the hit node's frame
+            lp_g = a.root.point_to_node(g.point, g.hit)
+            lp_w = b.root.point_to_node(w.point, w.hit)
+            np.testing.assert_allclose(g.hit.geometry.normal(lp_g), w.hit.geometry.normal(lp_w), rtol=0, atol=1e-9)
+        hits += len(got)
+    assert hits > 125  # the world sphere is hit by every ray: some rays hit the objects too
