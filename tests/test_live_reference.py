@@ -274,3 +274,64 @@ def test_scene_intersections_equal_the_reference(seed):
             np.testing.assert_allclose(g.hit.geometry.normal(lp_g), w.hit.geometry.normal(lp_w), rtol=0, atol=1e-9)
         hits += len(got)
     assert hits > 125  # the world sphere is hit by every ray: some rays hit the objects too
+
+
+# ---- the YAML front end on the reference's OWN scene files (examples/, tests/data/, the mkdocs tutorials) -------------
+def reference_yaml_parser():
+    """pvtrace.cli.parse of the reference, importable once the stub top-level package carries the names it imports."""
+    import sys
+
+    pkg = ref_loader.load_reference_package()
+    import pvtrace.geometry.mesh  # noqa: F401
+    for name, mod in (("Scene", "pvtrace.scene.scene"), ("Node", "pvtrace.scene.node"), ("Box", "pvtrace.geometry.box"),
+                      ("Mesh", "pvtrace.geometry.mesh"), ("Cylinder", "pvtrace.geometry.cylinder"),
+                      ("Sphere", "pvtrace.geometry.sphere"), ("Material", "pvtrace.material.material"),
+                      ("Absorber", "pvtrace.material.component"), ("Scatterer", "pvtrace.material.component"),
+                      ("Luminophore", "pvtrace.material.component"), ("Light", "pvtrace.light.light")):
+        __import__(mod)
+        setattr(pkg, name, getattr(sys.modules[mod], name))
+    pkg.MeshcatRenderer = object
+    import pvtrace.cli.parse as refparse
+
+    return refparse
+
+
+REFERENCE_YAML = ("examples/hello_world.yml", "examples/sphere_with_luminescent_dye.yml", "examples/studio_lsc.yml",
+                  "mkdocs/source/lsc_lumogen_red_cli/tutorial001.yml", "mkdocs/source/lsc_lumogen_red_cli/tutorial002.yml",
+                  "mkdocs/source/lsc_lumogen_red_cli/tutorial003.yml", "tests/data/simple_box.yml", "tests/data/simple_box2.yml")
+
+
+@pytest.mark.parametrize("path", REFERENCE_YAML)
+def test_yaml_front_end_on_the_reference_scene_files(path):
+    """Every scene file of the reference tree that the reference's own parser + compiler accept (pvtrace/cli/parse.py:72-551
+    incl. `record: true` desugaring, cli/parse.py:469-525): parsed by pvtrace_b200.cli.parse and flattened -- the same tables."""
+    import os
+
+    import pvtrace_b200 as pv
+    from pvtrace_b200.cli import parse as ourparse
+
+    full = os.path.join(ref_loader.REFERENCE_ROOT, path)
+    want = reference().compile_scene(reference_yaml_parser().parse(full))
+    got = pv.engine.compile_scene(ourparse.parse(full))
+    for table in scenes.TABLES:
+        g, w = np.asarray(getattr(got, table)), np.asarray(getattr(want, table))
+        assert g.shape == w.shape and g.dtype == w.dtype, (table, g.shape, w.shape, g.dtype, w.dtype)
+        np.testing.assert_allclose(g, w, rtol=1e-13, atol=1e-13, err_msg=table)
+    assert list(got.node_names) == list(want.node_names)
+    assert list(got.component_names) == list(want.component_names)
+    assert list(got.recorder_names) == list(want.recorder_names)
+
+
+def test_yaml_scene_with_histogram_sampled_spectra_is_rejected_like_the_reference():
+    import os
+
+    import pvtrace_b200 as pv
+    from pvtrace_b200.cli import parse as ourparse
+
+    full = os.path.join(ref_loader.REFERENCE_ROOT, "tests/data/lsc_scene.yml")
+    with pytest.raises(Exception) as theirs:
+        reference().compile_scene(reference_yaml_parser().parse(full))
+    with pytest.raises(pv.engine.UnsupportedSceneError) as mine:
+        pv.engine.compile_scene(ourparse.parse(full))
+    assert type(theirs.value).__name__ == "UnsupportedSceneError"
+    assert str(mine.value) == str(theirs.value)
