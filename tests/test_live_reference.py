@@ -335,3 +335,38 @@ def test_yaml_scene_with_histogram_sampled_spectra_is_rejected_like_the_referenc
         pv.engine.compile_scene(ourparse.parse(full))
     assert type(theirs.value).__name__ == "UnsupportedSceneError"
     assert str(mine.value) == str(theirs.value)
+
+
+@pytest.mark.skipif(ref_loader.load_ref_kernel() is None, reason="oracle/_ref not built on this machine")
+@pytest.mark.parametrize("seed", range(10))
+def test_host_result_classes_and_tally_restatement_on_the_reference_kernels_output(seed):
+    """EngineResult / RecorderResult / tally_histories of this package (the host side of the drop-in: pvtrace/engine/api.py:
+    26-194, tally.py:86-156) fed with what the COMPILED REFERENCE KERNEL returns for a random scene: the recorders read
+    from its tallies must equal the tallies recomputed from its event log by this package's restatement -- the reference's
+    own contract (tests/test_engine.py:204-318), across libraries."""
+    import pvtrace_b200 as pv
+    from pvtrace_b200.engine import tally_histories
+    from pvtrace_b200.engine.api import EngineResult
+
+    kernel = ref_loader.load_ref_kernel()
+    scene = random_scene(ours(), 700 + seed)
+    compiled = pv.engine.compile_scene(scene)
+    rng = np.random.default_rng(800 + seed)
+    n, m = 1500, 256
+    pos = rng.uniform(-6.0, 6.0, (n, 3))
+    direction = rng.normal(size=(n, 3))
+    direction /= np.linalg.norm(direction, axis=1)[:, None]
+    wl = rng.uniform(350.0, 850.0, n)
+    data = kernel.trace_bundle(compiled, pos, direction, wl, 5 + seed, 1000, m, seed % 3, 2, 1)
+    assert data["counts"].max() < m - 1
+    result = EngineResult(compiled, data, ["light"] * n, m, 1, 0.0)
+    got, want = result.recorders, tally_histories(scene, result.histories())
+    assert set(got) == set(want)
+    for key in got:
+        assert got[key].rays == want[key].rays and got[key].crossings == want[key].crossings, key
+        for i in range(len(got[key].spec.histograms)):
+            assert (got[key].histogram(i)[-1] == want[key].histogram(i)[-1]).all(), (key, i)
+        for prop in ("wavelength", "angle", "duration", "pathlength"):
+            if got[key].rays:
+                assert got[key].mean(prop) == pytest.approx(want[key].mean(prop), rel=1e-9, abs=1e-18), (key, prop)
+    assert sum(r.rays for r in got.values()) > n // 2  # (absorbed rays never reach the world's exit recorder)
